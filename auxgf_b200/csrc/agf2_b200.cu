@@ -1,0 +1,622 @@
+// libagf2_b200.so -- host side of the B200 moment build: work planner, TMA descriptors, launches,
+// and the C-ABI of include/agf2_b200.h.  Reference paths are relative to obackhouse/auxgf.
+//
+// Plan (replaces the `for i` loop of auxgf/lib/libagf2/optragf2.c:118 and its MPI split in
+// auxgf/mpi/agf2/optragf2.py:370-374):
+//   work items   DIAG(i)      X_ii                -> one column block  sqrt(os) X_ii
+//                PAIR(i>j)    X_ij, X_ji          -> two column blocks sqrt(os/2+ss)(X_ij-X_ji), sqrt(os/2)(X_ij+X_ji)
+//                OS(i,J)      X_iJ (other spin)   -> one column block  sqrt(os) X_iJ           (UHF only)
+//                ASYM(i,j)    j outside [istart,iend): U = X_ij -> W0, V = (c X_ij - s X_ji) -> W1
+//   items are dealt round-robin to `nparts` (one per GPU); each part packs its items into chunks whose
+//   column blocks fit the L2-sized workspace; per chunk: k1_form (integrals -> W), k2_moment (W -> vv, vev).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/agf2_b200.h"
+#include "moment_kernels.cuh"
+
+using namespace agf2;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? AGF2_B200_ENOMEM : AGF2_B200_ECUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                  \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+struct Ctx {
+    bool init = false;
+    int device = -1;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    EncodeTiledFn encode = nullptr;
+    int64_t ws_bytes = 40ll << 20;
+    bool simple = false;
+    bool profile = true;
+    // scratch
+    double* W[2] = {nullptr, nullptr};
+    size_t w_elems = 0;
+    double* E = nullptr;
+    size_t e_elems = 0;
+    double* acc = nullptr;   // 4 accumulators: S_vv, S_vev, A_vv, A_vev
+    size_t acc_elems = 0;
+    K1Tile* d_t1[2] = {nullptr, nullptr};
+    K1Tile* h_t1[2] = {nullptr, nullptr};
+    size_t t1_cap = 0;
+    cudaEvent_t t1_free[2] = {nullptr, nullptr};
+    K2Tile* d_t2 = nullptr;
+    size_t t2_cap = 0;
+    // staging for the host-pointer API
+    double* stage[8] = {nullptr};
+    size_t stage_elems[8] = {0};
+    // instrumentation
+    int64_t launches = 0;
+    std::vector<EventPair> events;
+    size_t events_used = 0;
+    double last_ms[2] = {0, 0};
+};
+Ctx g_ctx;
+
+int ensure_ctx() {
+    Ctx& c = g_ctx;
+    if (c.init) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(AGF2_B200_ENODEV, "no CUDA device visible (libagf2_b200 has no CPU fallback)");
+    if (c.device < 0) CU_TRY(cudaGetDevice(&c.device));
+    CU_TRY(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10)
+        return fail(AGF2_B200_ENODEV, std::string("device is sm_") + std::to_string(prop.major) +
+                                          std::to_string(prop.minor) + ", this library is built for sm_100a only");
+    c.num_sms = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (fn == nullptr || q != cudaDriverEntryPointSuccess)
+        return fail(AGF2_B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    c.encode = reinterpret_cast<EncodeTiledFn>(fn);
+    CU_TRY(cudaFuncSetAttribute(k1_form, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k2_moment, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    for (int b = 0; b < 2; ++b) CU_TRY(cudaEventCreateWithFlags(&c.t1_free[b], cudaEventDisableTiming));
+    if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
+    if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
+    c.init = true;
+    return 0;
+}
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need, bool zero) {
+    if (need <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    CU_TRY(cudaMalloc(&p, need * sizeof(T)));
+    if (zero) CU_TRY(cudaMemset(p, 0, need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
+int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_ctx.encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                              strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AGF2_B200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+struct Spin {            // one (Q|ja) tensor and its energies
+    const double* qja = nullptr;
+    int64_t ld = 0, nocc = 0, nvir = 0;
+    const double* ei = nullptr;   // host copies of the energies (planner needs e_i + e_j)
+    const double* ea_dev = nullptr;
+};
+
+struct Item { int kind, i, j; };   // kind: 0 DIAG, 1 PAIR, 2 OS, 3 ASYM
+struct SubTile { int i, j, a0, nb, bsel, esel, nv; long long col; double p, eij; };
+
+inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+void record(cudaStream_t st, int kind, bool begin) {
+    Ctx& c = g_ctx;
+    if (!c.profile) return;
+    if (begin) {
+        if (c.events_used == c.events.size()) {
+            EventPair p;
+            cudaEventCreate(&p.a);
+            cudaEventCreate(&p.b);
+            c.events.push_back(p);
+        }
+        c.events[c.events_used].kind = kind;
+        cudaEventRecord(c.events[c.events_used].a, st);
+    } else {
+        cudaEventRecord(c.events[c.events_used].b, st);
+        c.events_used++;
+    }
+}
+
+// The whole moment build on device-resident inputs.
+int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other,
+                const double* ei_same_host, const double* ei_other_host, int64_t nphys, int64_t naux,
+                int64_t istart, int64_t iend, double c_same, double s_same, double os_other, int64_t part,
+                int64_t nparts, double* vv, double* vev, cudaStream_t st)
+{
+    Ctx& c = g_ctx;
+    const int64_t o = same.nocc, v = same.nvir;
+    if (nphys <= 0 || naux <= 0 || o <= 0 || v <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    if (istart < 0 || iend > o || istart > iend) return fail(AGF2_B200_EINVAL, "bad [istart, iend)");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(AGF2_B200_EINVAL, "bad part/nparts");
+    if (c_same - s_same < 0 || c_same + s_same < 0 || os_other < 0)
+        return fail(AGF2_B200_EINVAL, "os_factor and ss_factor must be non-negative");
+    if ((ld_ixq & 1) || ld_ixq < naux || (same.ld & 1) || same.ld < v || (other && ((other->ld & 1) || other->ld < other->nvir)))
+        return fail(AGF2_B200_EINVAL, "leading dimensions must be even (16-byte TMA strides) and >= the row length");
+    if ((reinterpret_cast<uintptr_t>(ixq) & 15) || (reinterpret_cast<uintptr_t>(same.qja) & 15) ||
+        (other && (reinterpret_cast<uintptr_t>(other->qja) & 15)))
+        return fail(AGF2_B200_EINVAL, "device arrays must be 16-byte aligned");
+    if (nphys > (1 << 30) || naux > (1 << 30) || o * v > (1ll << 40)) return fail(AGF2_B200_EINVAL, "dimension too large");
+
+    const int64_t p_pad = rup(nphys, kTileM);
+    const int nxb = (int)(p_pad / kTileM);
+    const int nyb = (int)((nphys + kTileN - 1) / kTileN);
+    const int64_t vpad = rup(v, 8);
+    const int64_t vbpad = other ? rup(other->nvir, 8) : 0;
+    const double ca = std::sqrt(0.5 * (c_same + s_same)), cs = std::sqrt(0.5 * (c_same - s_same));
+    const double cd = std::sqrt(c_same - s_same), co = std::sqrt(os_other);
+
+    // ---- scratch ------------------------------------------------------------------------------
+    int64_t cap_cols = std::max<int64_t>(c.ws_bytes / (p_pad * 8), 2 * std::max(vpad, vbpad));
+    cap_cols = rup(cap_cols, 16);
+    const size_t w_need = (size_t)p_pad * cap_cols;
+    if (w_need > c.w_elems) {
+        for (int b = 0; b < 2; ++b) { if (c.W[b]) cudaFree(c.W[b]); c.W[b] = nullptr; }
+        c.w_elems = 0;
+        for (int b = 0; b < 2; ++b) {
+            CU_TRY(cudaMalloc(&c.W[b], w_need * 8));
+            CU_TRY(cudaMemset(c.W[b], 0, w_need * 8));
+        }
+        c.w_elems = w_need;
+    }
+    const int64_t ldw = cap_cols;
+    { int r = grow(c.E, c.e_elems, (size_t)cap_cols + 64, true); if (r) return r; }
+    { int r = grow(c.acc, c.acc_elems, (size_t)4 * p_pad * p_pad, false); if (r) return r; }
+    const size_t acc_n = (size_t)p_pad * p_pad;
+    double* S_vv = c.acc; double* S_vev = c.acc + acc_n; double* A_vv = c.acc + 2 * acc_n; double* A_vev = c.acc + 3 * acc_n;
+    CU_TRY(cudaMemsetAsync(c.acc, 0, 4 * acc_n * 8, st));
+
+    // ---- TMA descriptors of the inputs ----------------------------------------------------------
+    CUtensorMap mapA, mapB0, mapB1;
+    {
+        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)o};
+        cuuint64_t s[2] = {(cuuint64_t)ld_ixq * 8, (cuuint64_t)ld_ixq * 8 * (cuuint64_t)nphys};
+        cuuint32_t b[3] = {kKB, kTileM, 1};
+        if (int r = make_map(&mapA, ixq, 3, d, s, b)) return r;
+    }
+    {
+        cuuint64_t d[3] = {(cuuint64_t)v, (cuuint64_t)o, (cuuint64_t)naux};
+        cuuint64_t s[2] = {(cuuint64_t)same.ld * 8, (cuuint64_t)same.ld * 8 * (cuuint64_t)o};
+        cuuint32_t b[3] = {16, 1, kKB};
+        if (int r = make_map(&mapB0, same.qja, 3, d, s, b)) return r;
+    }
+    if (other) {
+        cuuint64_t d[3] = {(cuuint64_t)other->nvir, (cuuint64_t)other->nocc, (cuuint64_t)naux};
+        cuuint64_t s[2] = {(cuuint64_t)other->ld * 8, (cuuint64_t)other->ld * 8 * (cuuint64_t)other->nocc};
+        cuuint32_t b[3] = {16, 1, kKB};
+        if (int r = make_map(&mapB1, other->qja, 3, d, s, b)) return r;
+    } else {
+        mapB1 = mapB0;
+    }
+    const int nk1 = (int)((naux + kKB - 1) / kKB);
+
+    // ---- items of this part -----------------------------------------------------------------------
+    std::vector<Item> sym_items, asym_items;
+    {
+        int64_t n_diag = 0, n_pair = 0, n_os = 0, n_asym = 0;
+        for (int64_t i = istart; i < iend; ++i) {
+            if (cd != 0.0 && (n_diag++ % nparts) == part) sym_items.push_back({0, (int)i, (int)i});
+            for (int64_t j = istart; j < i; ++j)
+                if ((n_pair++ % nparts) == part) sym_items.push_back({1, (int)i, (int)j});
+            if (other && co != 0.0)
+                for (int64_t J = 0; J < other->nocc; ++J)
+                    if ((n_os++ % nparts) == part) sym_items.push_back({2, (int)i, (int)J});
+            for (int64_t j = 0; j < o; ++j)
+                if ((j < istart || j >= iend) && (n_asym++ % nparts) == part) asym_items.push_back({3, (int)i, (int)j});
+        }
+    }
+
+    // K2 tile lists (upper-triangle for symmetric chunks, all tiles for non-symmetric ones)
+    std::vector<K2Tile> t2_sym, t2_all;
+    for (int xb = 0; xb < nxb; ++xb)
+        for (int yb = 0; yb < nyb; ++yb) {
+            t2_all.push_back({xb, yb});
+            if (kTileN * yb + kTileN - 1 >= kTileM * xb) t2_sym.push_back({xb, yb});
+        }
+    { int r = grow(c.d_t2, c.t2_cap, t2_sym.size() + t2_all.size(), false); if (r) return r; }
+    CU_TRY(cudaMemcpyAsync(c.d_t2, t2_sym.data(), t2_sym.size() * sizeof(K2Tile), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c.d_t2 + t2_sym.size(), t2_all.data(), t2_all.size() * sizeof(K2Tile), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));   // t2 vectors are pageable host memory
+
+    c.events_used = 0;
+    int chunk_idx = 0;
+    std::vector<K1Tile> tiles;
+    std::vector<SubTile> plain;
+
+    auto run_chunks = [&](const std::vector<Item>& items, bool sym) -> int {
+        size_t pos = 0;
+        while (pos < items.size()) {
+            // ---- pack items into one chunk ----
+            tiles.clear();
+            plain.clear();
+            int64_t col = 0;
+            while (pos < items.size()) {
+                const Item& it = items[pos];
+                const int64_t w = it.kind == 2 ? vbpad : vpad;
+                const int nblk = it.kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
+                if (col + nblk * w > cap_cols) break;
+                if (it.kind == 1 || it.kind == 3) {
+                    const double eij = ei_same_host[it.i] + ei_same_host[it.j];
+                    const long long c1 = col, c2 = (it.kind == 1 && ca != 0.0) ? col + w : col;
+                    for (int64_t a0 = 0; a0 < vpad; a0 += kTileN) {
+                        const int nb = (int)std::min<int64_t>(8, (vpad - a0) / 8);
+                        const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, v - a0));
+                        for (int xb = 0; xb < nxb; ++xb) {
+                            K1Tile t;
+                            memset(&t, 0, sizeof(t));
+                            t.i1 = it.i; t.j1 = it.j; t.a1 = (int)a0; t.nb1 = nb;
+                            t.i2 = it.j; t.j2 = it.i; t.a2 = (int)a0; t.nb2 = nb;
+                            t.xb = xb; t.nv1 = t.nv2 = nv; t.e1 = t.e2 = eij;
+                            t.col1 = c1 + a0; t.col2 = c2 + a0;
+                            if (it.kind == 1) {
+                                t.ws1 = ca != 0.0 ? 0 : -1; t.p11 = ca; t.p12 = -ca;
+                                t.ws2 = cs != 0.0 ? 0 : -1; t.p21 = cs; t.p22 = cs;
+                            } else {
+                                t.ws1 = 0; t.p11 = 1.0; t.p12 = 0.0;
+                                t.ws2 = 1; t.p21 = c_same; t.p22 = -s_same;
+                                if (t.p21 == 0.0) t.p21 = 0.0;   // (c = 0: out2 width falls back to nb2 == nb1)
+                            }
+                            tiles.push_back(t);
+                        }
+                    }
+                } else {
+                    const bool os = it.kind == 2;
+                    const int64_t vv_ = os ? other->nvir : v;
+                    const double eij = ei_same_host[it.i] + (os ? ei_other_host[it.j] : ei_same_host[it.j]);
+                    for (int64_t a0 = 0; a0 < w; a0 += kTileN) {
+                        const int nb = (int)std::min<int64_t>(8, (w - a0) / 8);
+                        const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, vv_ - a0));
+                        plain.push_back({it.i, it.j, (int)a0, nb, os ? 1 : 0, os ? 1 : 0, nv, (long long)(col + a0),
+                                         os ? co : cd, eij});
+                    }
+                }
+                col += nblk * w;
+                ++pos;
+            }
+            if (col == 0) return fail(AGF2_B200_EINVAL, "workspace too small for one work item");
+            // two independent plain blocks share one CTA tile
+            std::stable_sort(plain.begin(), plain.end(), [](const SubTile& a, const SubTile& b) { return a.nb > b.nb; });
+            for (size_t k = 0; k < plain.size(); k += 2) {
+                const SubTile& s1 = plain[k];
+                const SubTile* s2 = k + 1 < plain.size() ? &plain[k + 1] : nullptr;
+                for (int xb = 0; xb < nxb; ++xb) {
+                    K1Tile t;
+                    memset(&t, 0, sizeof(t));
+                    t.xb = xb;
+                    t.i1 = s1.i; t.j1 = s1.j; t.a1 = s1.a0; t.nb1 = s1.nb; t.bsel1 = s1.bsel; t.esel1 = s1.esel;
+                    t.nv1 = s1.nv; t.col1 = s1.col; t.p11 = s1.p; t.e1 = s1.eij; t.ws1 = 0;
+                    t.ws2 = -1;
+                    if (s2) {
+                        t.i2 = s2->i; t.j2 = s2->j; t.a2 = s2->a0; t.nb2 = s2->nb; t.bsel2 = s2->bsel; t.esel2 = s2->esel;
+                        t.nv2 = s2->nv; t.col2 = s2->col; t.p22 = s2->p; t.e2 = s2->eij; t.ws2 = 0;
+                    }
+                    tiles.push_back(t);
+                }
+            }
+            std::stable_sort(tiles.begin(), tiles.end(),
+                             [](const K1Tile& a, const K1Tile& b) { return a.nb1 + a.nb2 > b.nb1 + b.nb2; });
+
+            // ---- upload the tile list (double-buffered pinned staging) ----
+            const int buf = chunk_idx & 1;
+            if (tiles.size() > c.t1_cap) {
+                CU_TRY(cudaStreamSynchronize(st));
+                for (int b = 0; b < 2; ++b) {
+                    if (c.d_t1[b]) cudaFree(c.d_t1[b]);
+                    if (c.h_t1[b]) cudaFreeHost(c.h_t1[b]);
+                    c.d_t1[b] = nullptr; c.h_t1[b] = nullptr;
+                }
+                c.t1_cap = 0;
+                const size_t cap = tiles.size() * 2 + 1024;
+                for (int b = 0; b < 2; ++b) {
+                    CU_TRY(cudaMalloc(&c.d_t1[b], cap * sizeof(K1Tile)));
+                    CU_TRY(cudaMallocHost(&c.h_t1[b], cap * sizeof(K1Tile)));
+                }
+                c.t1_cap = cap;
+            } else if (chunk_idx >= 2) {
+                CU_TRY(cudaEventSynchronize(c.t1_free[buf]));
+            }
+            memcpy(c.h_t1[buf], tiles.data(), tiles.size() * sizeof(K1Tile));
+            CU_TRY(cudaMemcpyAsync(c.d_t1[buf], c.h_t1[buf], tiles.size() * sizeof(K1Tile), cudaMemcpyHostToDevice, st));
+
+            // ---- K1: form the integral blocks of this chunk ----
+            record(st, 0, true);
+            if (!c.simple) {
+                k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, st>>>(
+                    mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev, c.W[0], c.W[1],
+                    c.E, ldw, nk1);
+            } else {
+                k1_form_simple<<<(unsigned)tiles.size(), 256, 0, st>>>(
+                    ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,
+                    other ? other->qja : same.qja, other ? other->ld : same.ld, other ? (int)other->nocc : (int)o,
+                    other ? (int)other->nvir : (int)v, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
+                    c.W[0], c.W[1], c.E, ldw);
+            }
+            record(st, 0, false);
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaEventRecord(c.t1_free[buf], st));
+            c.launches++;
+
+            // ---- K2: accumulate the moments of this chunk ----
+            const std::vector<K2Tile>& t2 = sym ? t2_sym : t2_all;
+            const K2Tile* d_t2 = sym ? c.d_t2 : c.d_t2 + t2_sym.size();
+            const int nk2 = (int)((col + kKB - 1) / kKB);
+            int nsplit = (int)((2 * c.num_sms + (int)t2.size() - 1) / (int)t2.size());
+            nsplit = std::max(1, std::min(nsplit, std::max(1, nk2 / 8)));
+            record(st, 1, true);
+            if (!c.simple) {
+                CUtensorMap mapWA, mapWB;
+                cuuint64_t d[2] = {(cuuint64_t)col, (cuuint64_t)p_pad};
+                cuuint64_t s[1] = {(cuuint64_t)ldw * 8};
+                cuuint32_t b[2] = {kKB, 64};
+                if (int r = make_map(&mapWA, c.W[0], 2, d, s, b)) return r;
+                if (int r = make_map(&mapWB, sym ? c.W[0] : c.W[1], 2, d, s, b)) return r;
+                dim3 grid((unsigned)t2.size(), (unsigned)nsplit);
+                k2_moment<<<grid, kThreads, kK2SmemBytes, st>>>(mapWA, mapWB, c.E, d_t2, sym ? S_vv : A_vv,
+                                                               sym ? S_vev : A_vev, p_pad, nk2, nsplit);
+            } else {
+                k2_moment_simple<<<(unsigned)t2.size(), 256, 0, st>>>(c.W[0], sym ? c.W[0] : c.W[1], ldw, c.E, (int)col,
+                                                                      d_t2, sym ? S_vv : A_vv, sym ? S_vev : A_vev, p_pad);
+            }
+            record(st, 1, false);
+            CU_TRY(cudaGetLastError());
+            c.launches++;
+            ++chunk_idx;
+        }
+        return 0;
+    };
+
+    if (int r = run_chunks(sym_items, true)) return r;
+    if (int r = run_chunks(asym_items, false)) return r;
+
+    dim3 g3((unsigned)((nphys + 127) / 128), (unsigned)nphys);
+    k3_finalize<<<g3, 128, 0, st>>>(S_vv, S_vev, asym_items.empty() ? nullptr : A_vv, asym_items.empty() ? nullptr : A_vev,
+                                    p_pad, (int)nphys, vv, vev);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return 0;
+}
+
+int finish_profile(cudaStream_t st) {
+    Ctx& c = g_ctx;
+    CU_TRY(cudaStreamSynchronize(st));
+    c.last_ms[0] = c.last_ms[1] = 0;
+    for (size_t k = 0; k < c.events_used; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c.events[k].a, c.events[k].b);
+        c.last_ms[c.events[k].kind] += ms;
+    }
+    c.events_used = 0;
+    return 0;
+}
+
+// copy a host matrix (rows x cols, contiguous) into a device staging slot with an even pitch
+int stage_in(int slot, const double* host, int64_t rows, int64_t cols, int64_t* ld_out, cudaStream_t st) {
+    Ctx& c = g_ctx;
+    const int64_t ld = rup(cols, 2);
+    if (int r = grow(c.stage[slot], c.stage_elems[slot], (size_t)std::max<int64_t>(rows * ld, 2), false)) return r;
+    CU_TRY(cudaMemcpy2DAsync(c.stage[slot], ld * 8, host, cols * 8, cols * 8, rows, cudaMemcpyHostToDevice, st));
+    *ld_out = ld;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* agf2_b200_last_error(void) { return g_err.c_str(); }
+const char* agf2_b200_version(void) { return "agf2_b200 0.1 (sm_100a; DMMA.8x8x4 + TMA)"; }
+
+int agf2_b200_set_device(int device) {
+    if (g_ctx.init && g_ctx.device != device) return fail(AGF2_B200_EINVAL, "context already bound to another device");
+    g_ctx.device = device;
+    return 0;
+}
+
+int agf2_b200_set_workspace_bytes(int64_t bytes) {
+    if (bytes < (1 << 20)) return fail(AGF2_B200_EINVAL, "workspace must be at least 1 MiB");
+    g_ctx.ws_bytes = bytes;
+    return 0;
+}
+
+int agf2_b200_set_simple_kernels(int on) {
+    g_ctx.simple = on != 0;
+    return 0;
+}
+
+int64_t agf2_b200_launch_count(int reset) {
+    const int64_t n = g_ctx.launches;
+    if (reset) g_ctx.launches = 0;
+    return n;
+}
+
+int agf2_b200_last_kernel_ms(double* k1, double* k2) {
+    if (k1) *k1 = g_ctx.last_ms[0];
+    if (k2) *k2 = g_ctx.last_ms[1];
+    return 0;
+}
+
+int agf2_b200_moments_rhf_dev(const double* ixq, int64_t ld_ixq, const double* qja, int64_t ld_qja, const double* ei,
+                              const double* ea, int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux,
+                              int64_t istart, int64_t iend, double os_factor, double ss_factor, int64_t part,
+                              int64_t nparts, double* vv, double* vev, void* stream, int sync)
+{
+    if (int r = ensure_ctx()) return r;
+    if (!ixq || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
+    if (nocc <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    std::vector<double> ei_h((size_t)nocc);
+    CU_TRY(cudaMemcpyAsync(ei_h.data(), ei, nocc * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    Spin same;
+    same.qja = qja; same.ld = ld_qja; same.nocc = nocc; same.nvir = nvir; same.ea_dev = ea;
+    int r = run_moments(ixq, ld_ixq, same, nullptr, ei_h.data(), nullptr, nphys, naux, istart, iend,
+                        os_factor + ss_factor, ss_factor, 0.0, part, nparts, vv, vev, st);
+    if (r) return r;
+    if (sync) return finish_profile(st);
+    return 0;
+}
+
+int agf2_b200_moments_uhf_dev(const double* ixq_a, int64_t ld_ixq, const double* qja_a, int64_t ld_qja_a,
+                              const double* qja_b, int64_t ld_qja_b, const double* ei_a, const double* ei_b,
+                              const double* ea_a, const double* ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                              int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart, int64_t iend,
+                              double os_factor, double ss_factor, int64_t part, int64_t nparts, double* vv,
+                              double* vev, void* stream, int sync)
+{
+    if (int r = ensure_ctx()) return r;
+    if (!ixq_a || !qja_a || !ei_a || !ea_a || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
+    if (nocc_a <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    const bool has_b = nocc_b > 0 && nvir_b > 0;
+    if (has_b && (!qja_b || !ei_b || !ea_b)) return fail(AGF2_B200_EINVAL, "null pointer");
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    std::vector<double> eia((size_t)nocc_a), eib((size_t)std::max<int64_t>(nocc_b, 1));
+    CU_TRY(cudaMemcpyAsync(eia.data(), ei_a, nocc_a * 8, cudaMemcpyDeviceToHost, st));
+    if (has_b) CU_TRY(cudaMemcpyAsync(eib.data(), ei_b, nocc_b * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    Spin same, other;
+    same.qja = qja_a; same.ld = ld_qja_a; same.nocc = nocc_a; same.nvir = nvir_a; same.ea_dev = ea_a;
+    other.qja = qja_b; other.ld = ld_qja_b; other.nocc = nocc_b; other.nvir = nvir_b; other.ea_dev = ea_b;
+    // same-spin: Coulomb ss, exchange ss (optuagf2.c:211-256); opposite spin: Coulomb os
+    int r = run_moments(ixq_a, ld_ixq, same, has_b ? &other : nullptr, eia.data(), eib.data(), nphys, naux, istart,
+                        iend, ss_factor, ss_factor, os_factor, part, nparts, vv, vev, st);
+    if (r) return r;
+    if (sync) return finish_profile(st);
+    return 0;
+}
+
+int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const double* ei, const double* ea,
+                                  int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t istart,
+                                  int64_t iend, double os_factor, double ss_factor, double* vv, double* vev)
+{
+    if (int r = ensure_ctx()) return r;
+    if (!ixq || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
+    if (nphys <= 0 || nocc <= 0 || nvir <= 0 || naux <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    if (istart >= iend) return 0;
+    Ctx& c = g_ctx;
+    cudaStream_t st = c.stream;
+    int64_t ld_ixq, ld_qja, ld1;
+    if (int r = stage_in(0, ixq, nocc * nphys, naux, &ld_ixq, st)) return r;
+    if (int r = stage_in(1, qja, naux * nocc, nvir, &ld_qja, st)) return r;   // (naux*nocc) rows of nvir
+    if (int r = stage_in(2, ei, 1, nocc, &ld1, st)) return r;
+    if (int r = stage_in(3, ea, 1, nvir, &ld1, st)) return r;
+    if (int r = grow(c.stage[4], c.stage_elems[4], (size_t)2 * nphys * nphys, false)) return r;
+    CU_TRY(cudaMemsetAsync(c.stage[4], 0, (size_t)2 * nphys * nphys * 8, st));
+    double* dvv = c.stage[4];
+    double* dvev = c.stage[4] + nphys * nphys;
+    int r = agf2_b200_moments_rhf_dev(c.stage[0], ld_ixq, c.stage[1], ld_qja, c.stage[2], c.stage[3], nphys, nocc, nvir,
+                                      naux, istart, iend, os_factor, ss_factor, 0, 1, dvv, dvev, st, 1);
+    if (r) return r;
+    std::vector<double> h((size_t)2 * nphys * nphys);
+    CU_TRY(cudaMemcpy(h.data(), c.stage[4], h.size() * 8, cudaMemcpyDeviceToHost));
+    const size_t n = (size_t)nphys * nphys;
+    for (size_t k = 0; k < n; ++k) { vv[k] += h[k]; vev[k] += h[n + k]; }   // `+=` as optragf2.c:305-309
+    return 0;
+}
+
+int agf2_b200_build_part_loop_uhf(const double* ixq_a, const double* qja_a, const double* qja_b, const double* ei_a,
+                                  const double* ei_b, const double* ea_a, const double* ea_b, int64_t nphys,
+                                  int64_t nocc_a, int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
+                                  int64_t istart, int64_t iend, double os_factor, double ss_factor, double* vv,
+                                  double* vev)
+{
+    if (int r = ensure_ctx()) return r;
+    if (!ixq_a || !qja_a || !ei_a || !ea_a || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
+    if (nphys <= 0 || nocc_a <= 0 || nvir_a <= 0 || naux <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    if (istart >= iend) return 0;
+    Ctx& c = g_ctx;
+    cudaStream_t st = c.stream;
+    const bool has_b = nocc_b > 0 && nvir_b > 0;
+    int64_t ld_ixq, ld_qa, ld_qb = 2, ld1;
+    if (int r = stage_in(0, ixq_a, nocc_a * nphys, naux, &ld_ixq, st)) return r;
+    if (int r = stage_in(1, qja_a, naux * nocc_a, nvir_a, &ld_qa, st)) return r;
+    if (int r = stage_in(2, ei_a, 1, nocc_a, &ld1, st)) return r;
+    if (int r = stage_in(3, ea_a, 1, nvir_a, &ld1, st)) return r;
+    if (has_b) {
+        if (int r = stage_in(5, qja_b, naux * nocc_b, nvir_b, &ld_qb, st)) return r;
+        if (int r = stage_in(6, ei_b, 1, nocc_b, &ld1, st)) return r;
+        if (int r = stage_in(7, ea_b, 1, nvir_b, &ld1, st)) return r;
+    }
+    if (int r = grow(c.stage[4], c.stage_elems[4], (size_t)2 * nphys * nphys, false)) return r;
+    CU_TRY(cudaMemsetAsync(c.stage[4], 0, (size_t)2 * nphys * nphys * 8, st));
+    double* dvv = c.stage[4];
+    double* dvev = c.stage[4] + nphys * nphys;
+    int r = agf2_b200_moments_uhf_dev(c.stage[0], ld_ixq, c.stage[1], ld_qa, has_b ? c.stage[5] : nullptr, ld_qb,
+                                      c.stage[2], has_b ? c.stage[6] : nullptr, c.stage[3], has_b ? c.stage[7] : nullptr,
+                                      nphys, nocc_a, has_b ? nocc_b : 0, nvir_a, has_b ? nvir_b : 0, naux, istart, iend,
+                                      os_factor, ss_factor, 0, 1, dvv, dvev, st, 1);
+    if (r) return r;
+    std::vector<double> h((size_t)2 * nphys * nphys);
+    CU_TRY(cudaMemcpy(h.data(), c.stage[4], h.size() * 8, cudaMemcpyDeviceToHost));
+    const size_t n = (size_t)nphys * nphys;
+    for (size_t k = 0; k < n; ++k) { vv[k] += h[k]; vev[k] += h[n + k]; }
+    return 0;
+}
+
+// ---- drop-in symbols (reference signatures) ---------------------------------------------------------
+static void die(const char* fn) {
+    fprintf(stderr, "libagf2_b200: %s failed: %s (no CPU fallback)\n", fn, g_err.c_str());
+    abort();
+}
+
+void build_part_loop_rhf(double* ixq, double* qja, double* ei, double* ea, uint32_t nphys, uint32_t nocc,
+                         uint32_t nvir, uint32_t naux, uint32_t istart, uint32_t iend, double* vv, double* vev)
+{
+    if (agf2_b200_build_part_loop_rhf(ixq, qja, ei, ea, nphys, nocc, nvir, naux, istart, iend, 1.0, 1.0, vv, vev))
+        die("build_part_loop_rhf");
+}
+
+void build_part_loop_uhf(double* ixq_a, double* qja_a, double* qja_b, double* ei_a, double* ei_b, double* ea_a,
+                         double* ea_b, uint32_t nphys, uint32_t nocc_a, uint32_t nocc_b, uint32_t nvir_a,
+                         uint32_t nvir_b, uint32_t naux, uint32_t istart, uint32_t iend, double* vv, double* vev)
+{
+    if (agf2_b200_build_part_loop_uhf(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a, nocc_b, nvir_a,
+                                      nvir_b, naux, istart, iend, 1.0, 1.0, vv, vev))
+        die("build_part_loop_uhf");
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+"""ctypes loader of libagf2_b200.so -- the B200 counterpart of ``auxgf/lib/agf2.py``.
+
+Mirrors the reference shim (``auxgf/lib/agf2.py:63-145``): same function names, same argument
+meaning (``gf_occ``/``gf_vir`` are ``Aux``-like objects exposing ``naux``, ``nphys``, ``e``), same
+``vv``/``vev`` accumulate-and-return behaviour, and -- like the reference (``agf2.py:18-21``) --
+a missing shared library is a ``RuntimeError`` at import time.  There is no CPU fallback: the
+compute entry points raise ``Agf2B200Error`` when no sm_100 device is present.
+
+Extra (not in the reference): ``os_factor``/``ss_factor`` keywords (SCS, ``auxgf/aux/dfrmp2.py:82-84``)
+and the device-resident calls used by ``auxgf_b200.agf2`` so that the DF tensors stay in HBM.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.realpath(__file__))
+LIB_PATH = os.path.join(_HERE, "libagf2_b200.so")
+
+_f64 = np.float64
+_in2 = np.ctypeslib.ndpointer(dtype=_f64, ndim=2, flags="C,A")
+_in1 = np.ctypeslib.ndpointer(dtype=_f64, ndim=1, flags="C,A")
+_out2 = np.ctypeslib.ndpointer(dtype=_f64, ndim=2, flags="C,A,W")
+_i64 = ctypes.c_int64
+_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# every symbol include/agf2_b200.h declares (tests check they are all exported)
+SYMBOLS = [
+    "build_part_loop_rhf", "build_part_loop_uhf", "agf2_b200_last_error", "agf2_b200_version",
+    "agf2_b200_set_device", "agf2_b200_set_workspace_bytes", "agf2_b200_build_part_loop_rhf",
+    "agf2_b200_build_part_loop_uhf", "agf2_b200_moments_rhf_dev", "agf2_b200_moments_uhf_dev",
+    "agf2_b200_compress", "agf2_b200_eigh", "agf2_b200_launch_count", "agf2_b200_last_kernel_ms",
+    "agf2_b200_set_simple_kernels",
+]
+
+
+class Agf2B200Error(RuntimeError):
+    pass
+
+
+def _load():
+    try:
+        clib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        print(e)
+        raise RuntimeError("Cannot locate agf2_b200 CUDA library (%s); build it with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                           "`make -C auxgf_b200/csrc`." % LIB_PATH)
+    return clib
+
+
+_libagf2 = _load()
+
+_libagf2.agf2_b200_last_error.restype = ctypes.c_char_p
+_libagf2.agf2_b200_solver_last_error.restype = ctypes.c_char_p
+_libagf2.agf2_b200_version.restype = ctypes.c_char_p
+_libagf2.agf2_b200_launch_count.restype = _i64
+_libagf2.agf2_b200_launch_count.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_last_kernel_ms.argtypes = [ctypes.POINTER(_dbl), ctypes.POINTER(_dbl)]
+_libagf2.agf2_b200_set_device.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_set_workspace_bytes.argtypes = [_i64]
+_libagf2.agf2_b200_set_simple_kernels.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_build_part_loop_rhf.argtypes = [_in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_build_part_loop_uhf.argtypes = [_in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_i64] * 8 + \
+    [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_moments_rhf_dev.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp] + [_i64] * 6 + [_dbl, _dbl, _i64, _i64,
+                                                                                             _vp, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_moments_uhf_dev.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp] + [_i64] * 8 + \
+    [_dbl, _dbl, _i64, _i64, _vp, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_compress.argtypes = [_vp, _vp, _i64, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_eigh.argtypes = [_vp, _i64, _vp, _vp, ctypes.c_int]
+# the reference's own void symbols (drop-in ABI; argtypes as auxgf/lib/agf2.py:28-60)
+_u32 = ctypes.c_uint32
+_libagf2.build_part_loop_rhf.restype = None
+_libagf2.build_part_loop_rhf.argtypes = [_in2, _in2, _in1, _in1] + [_u32] * 6 + [_out2, _out2]
+_libagf2.build_part_loop_uhf.restype = None
+_libagf2.build_part_loop_uhf.argtypes = [_in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_u32] * 8 + [_out2, _out2]
+
+
+def check(status):
+    if status != 0:
+        msg = _libagf2.agf2_b200_last_error().decode() or _libagf2.agf2_b200_solver_last_error().decode()
+        raise Agf2B200Error("libagf2_b200 error %d: %s" % (status, msg))
+
+
+def version():
+    return _libagf2.agf2_b200_version().decode()
+
+
+def launch_count(reset=False):
+    return int(_libagf2.agf2_b200_launch_count(1 if reset else 0))
+
+
+def last_kernel_ms():
+    a, b = _dbl(0), _dbl(0)
+    _libagf2.agf2_b200_last_kernel_ms(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def set_simple_kernels(on):
+    check(_libagf2.agf2_b200_set_simple_kernels(1 if on else 0))
+
+
+def set_workspace_bytes(nbytes):
+    check(_libagf2.agf2_b200_set_workspace_bytes(int(nbytes)))
+
+
+def _c(a, ndim):
+    a = np.ascontiguousarray(a, dtype=_f64)
+    assert a.ndim == ndim
+    return a
+
+
+def build_part_loop_rhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None,
+                        os_factor=1.0, ss_factor=1.0):
+    """Inner loop of ``OptRAGF2.build_part`` on the GPU (signature of auxgf/lib/agf2.py:63)."""
+    nocc = gf_occ.naux
+    nvir = gf_vir.naux
+    nphys = gf_occ.nphys
+
+    ei = _c(gf_occ.e, 1)
+    ea = _c(gf_vir.e, 1)
+
+    ixq = _c(np.asarray(ixq).reshape(nocc * nphys, -1), 2)
+    qja = _c(np.asarray(qja).reshape(-1, nocc * nvir), 2)
+    naux = qja.shape[0]
+
+    if vv is None:
+        vv = np.zeros((nphys, nphys), dtype=_f64, order="C")
+    if vev is None:
+        vev = np.zeros((nphys, nphys), dtype=_f64, order="C")
+    vv = np.ascontiguousarray(vv)
+    vev = np.ascontiguousarray(vev)
+
+    check(_libagf2.agf2_b200_build_part_loop_rhf(ixq, qja, ei, ea, nphys, nocc, nvir, naux, istart, iend,
+                                                 os_factor, ss_factor, vv, vev))
+    return vv, vev
+
+
+def build_part_loop_uhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None,
+                        os_factor=1.0, ss_factor=1.0):
+    """Inner loop of ``OptUAGF2.build_part`` for one spin channel (auxgf/lib/agf2.py:102)."""
+    nocc_a = gf_occ[0].naux
+    nocc_b = gf_occ[1].naux
+    nvir_a = gf_vir[0].naux
+    nvir_b = gf_vir[1].naux
+    nphys = gf_occ[0].nphys
+
+    ei_a = _c(gf_occ[0].e, 1)
+    ei_b = _c(gf_occ[1].e, 1)
+    ea_a = _c(gf_vir[0].e, 1)
+    ea_b = _c(gf_vir[1].e, 1)
+
+    ixq_a = _c(np.asarray(ixq[0]).reshape(nocc_a * nphys, -1), 2)
+    qja_a = _c(np.asarray(qja[0]).reshape(-1, nocc_a * nvir_a), 2)
+    naux = qja_a.shape[0]
+    qja_b = _c(np.asarray(qja[1]).reshape(naux, nocc_b * nvir_b), 2)
+
+    if vv is None:
+        vv = np.zeros((nphys, nphys), dtype=_f64, order="C")
+    if vev is None:
+        vev = np.zeros((nphys, nphys), dtype=_f64, order="C")
+    vv = np.ascontiguousarray(vv)
+    vev = np.ascontiguousarray(vev)
+
+    check(_libagf2.agf2_b200_build_part_loop_uhf(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a, nocc_b,
+                                                 nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor, vv, vev))
+    return vv, vev
+
+
+# ---- raw-array conveniences (no Aux objects) --------------------------------------------------
+class _Poles:
+    def __init__(self, e, nphys):
+        self.e = np.asarray(e, dtype=_f64)
+        self.naux = self.e.size
+        self.nphys = nphys
+
+
+def moments_rhf(ixq, qja, ei, ea, nphys, istart=0, iend=None, os_factor=1.0, ss_factor=1.0):
+    occ, vir = _Poles(ei, nphys), _Poles(ea, nphys)
+    return build_part_loop_rhf(ixq, qja, occ, vir, istart, occ.naux if iend is None else iend,
+                               os_factor=os_factor, ss_factor=ss_factor)
+
+
+def moments_uhf(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, istart=0, iend=None,
+                os_factor=1.0, ss_factor=1.0):
+    occ = (_Poles(ei_a, nphys), _Poles(ei_b, nphys))
+    vir = (_Poles(ea_a, nphys), _Poles(ea_b, nphys))
+    return build_part_loop_uhf((ixq_a, None), (qja_a, qja_b), occ, vir, istart,
+                               occ[0].naux if iend is None else iend, os_factor=os_factor, ss_factor=ss_factor)
+
+
+def compress(vv, vev):
+    """Device pole compression (auxgf/agf2/optragf2.py:270-278) on host arrays -> (e, c)."""
+    vv = _c(vv, 2); vev = _c(vev, 2)
+    n = vv.shape[0]
+    e = np.empty(n); c = np.empty((n, n))
+    check(_libagf2.agf2_b200_compress(vv.ctypes.data, vev.ctypes.data, n, e.ctypes.data, c.ctypes.data, 0))
+    return e, c
+
+
+def eigh(a):
+    """cuSOLVER dsyevd on a host symmetric matrix (auxgf/aux/eig.py:23-33) -> (w, v)."""
+    a = _c(a, 2)
+    n = a.shape[0]
+    w = np.empty(n); v = np.empty((n, n))
+    check(_libagf2.agf2_b200_eigh(a.ctypes.data, n, w.ctypes.data, v.ctypes.data, 0))
+    return w, v

@@ -1,0 +1,143 @@
+/*
+ * agf2_b200.h -- C-ABI of libagf2_b200.so: the B200 (sm_100a) replacement for the reference's
+ * native moment-build library  auxgf/lib/libagf2/agf2.so  (reference paths are relative to the
+ * obackhouse/auxgf source tree).
+ *
+ * Two layers:
+ *
+ *  (1) DROP-IN symbols with the reference's exact names and signatures (host pointers, `+=`
+ *      semantics, [istart, iend) slice of the occupied-pole loop).  A build of auxgf can load this
+ *      library in place of agf2.so without touching auxgf/lib/agf2.py:
+ *          build_part_loop_rhf   replaces  auxgf/lib/libagf2/optragf2.c:32-43
+ *          build_part_loop_uhf   replaces  auxgf/lib/libagf2/optuagf2.c:31-47
+ *      They return void like the reference; a failure (no CUDA device, CUDA error) prints the
+ *      message to stderr and aborts -- there is NO CPU fallback.
+ *
+ *  (2) STATUS-RETURNING entry points (`agf2_b200_*`): same arithmetic, 64-bit sizes, explicit
+ *      SCS factors, device-resident variants (inputs already in HBM, no host<->device copies),
+ *      the on-device pole compression (cuSOLVER potrf/trsm/syevd; replaces the NumPy
+ *      cholesky/inv/eigh of auxgf/agf2/optragf2.py:270-278) and a dense symmetric eigensolver for
+ *      the extended Fock matrix (replaces np.linalg.eigh in auxgf/aux/eig.py:23-33).
+ *      Return value: 0 on success, an AGF2_B200_E* code otherwise; agf2_b200_last_error() gives
+ *      the text.  All calls are made from one host thread per device context; the library owns its
+ *      CUDA streams and scratch memory.
+ *
+ * Array conventions (identical to the reference, auxgf/lib/agf2.py:63-145):
+ *      ixq   (nocc*nphys, naux)   row-major f64,  element [(i, x), Q]     = (i x | Q)
+ *      qja   (naux, nocc*nvir)    row-major f64,  element [Q, (j, a)]     = (Q | j a)
+ *      ei    (nocc)  energies of the poles playing the "occupied" role,  ea (nvir) the "virtual" role
+ *      vv, vev (nphys, nphys)     row-major f64,  accumulated into (+=)
+ * Arithmetic (auxgf/lib/libagf2/optragf2.c:117-295), with X[x,i,j,a] = sum_Q ixq[i,x,Q] qja[Q,j,a]:
+ *      vv [x,y] += sum_{i in [istart,iend)} sum_{j,a} X[x,i,j,a] ( (os+ss) X[y,i,j,a] - ss X[y,j,i,a] )
+ *      vev[x,y] += the same with the weight (ei[i] + ei[j] - ea[a])
+ *   the reference hard-codes os = ss = 1 (optragf2.c:217,237); os/ss enter as in
+ *   auxgf/aux/dfrmp2.py:82-84.
+ */
+#ifndef AGF2_B200_H
+#define AGF2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    AGF2_B200_OK = 0,
+    AGF2_B200_ENODEV = 1,    /* no CUDA device / not sm_100 */
+    AGF2_B200_ECUDA = 2,     /* CUDA runtime / driver error */
+    AGF2_B200_EINVAL = 3,    /* bad argument (sizes, alignment, null pointer) */
+    AGF2_B200_ENOMEM = 4,    /* device allocation failed */
+    AGF2_B200_ENOTSPD = 5,   /* vv is not positive definite (Cholesky failed; reference raises LinAlgError) */
+    AGF2_B200_ESOLVER = 6    /* cuSOLVER / cuBLAS failure */
+};
+
+/* ---- (1) drop-in symbols: reference signatures, host memory -------------------------------- */
+
+/* replaces auxgf/lib/libagf2/optragf2.c:32-43 */
+void build_part_loop_rhf(double *ixq, double *qja, double *ei, double *ea,
+                         uint32_t nphys, uint32_t nocc, uint32_t nvir, uint32_t naux,
+                         uint32_t istart, uint32_t iend, double *vv, double *vev);
+
+/* replaces auxgf/lib/libagf2/optuagf2.c:31-47 */
+void build_part_loop_uhf(double *ixq_a, double *qja_a, double *qja_b,
+                         double *ei_a, double *ei_b, double *ea_a, double *ea_b,
+                         uint32_t nphys, uint32_t nocc_a, uint32_t nocc_b,
+                         uint32_t nvir_a, uint32_t nvir_b, uint32_t naux,
+                         uint32_t istart, uint32_t iend, double *vv, double *vev);
+
+/* ---- (2) status-returning API --------------------------------------------------------------- */
+
+const char *agf2_b200_last_error(void);
+const char *agf2_b200_version(void);
+
+/* Select the CUDA device this thread's context uses (default: current device). */
+int agf2_b200_set_device(int device);
+
+/* Workspace for the (xi|ja) chunk that flows between the two kernels, in bytes per buffer
+ * (two buffers are kept).  Default 40 MiB each so that both stay resident in the 126 MB L2. */
+int agf2_b200_set_workspace_bytes(int64_t bytes);
+
+/* Host-memory variants with SCS factors and 64-bit sizes (copies inputs to HBM, runs, adds the
+ * result into the host vv/vev). */
+int agf2_b200_build_part_loop_rhf(const double *ixq, const double *qja, const double *ei,
+                                  const double *ea, int64_t nphys, int64_t nocc, int64_t nvir,
+                                  int64_t naux, int64_t istart, int64_t iend, double os_factor,
+                                  double ss_factor, double *vv, double *vev);
+
+int agf2_b200_build_part_loop_uhf(const double *ixq_a, const double *qja_a, const double *qja_b,
+                                  const double *ei_a, const double *ei_b, const double *ea_a,
+                                  const double *ea_b, int64_t nphys, int64_t nocc_a,
+                                  int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
+                                  int64_t istart, int64_t iend, double os_factor,
+                                  double ss_factor, double *vv, double *vev);
+
+/* Device-resident variants: every pointer is DEVICE memory on the selected device.
+ *   ixq : (nocc, nphys, ld_ixq) with ld_ixq >= naux, ld_ixq even   (row pitch in doubles)
+ *   qja : (naux, nocc, ld_qja)  with ld_qja >= nvir, ld_qja even
+ *   vv, vev : (nphys, nphys) contiguous, accumulated into (+=).
+ * Work on the pole slice [istart, iend) can be restricted further to the pair-work items
+ * [part, nparts) -- items are dealt round-robin -- which is how the moment build is sharded over
+ * the GPUs of one box (replaces the MPI split of auxgf/mpi/agf2/optragf2.py:370-374); the caller
+ * sums the per-GPU vv/vev (one all-reduce).  Use part = 0, nparts = 1 for everything.
+ * `stream` is a cudaStream_t (0 = the library's own stream); the call is asynchronous with
+ * respect to the host unless `sync` is non-zero. */
+int agf2_b200_moments_rhf_dev(const double *ixq, int64_t ld_ixq, const double *qja, int64_t ld_qja,
+                              const double *ei, const double *ea, int64_t nphys, int64_t nocc,
+                              int64_t nvir, int64_t naux, int64_t istart, int64_t iend,
+                              double os_factor, double ss_factor, int64_t part, int64_t nparts,
+                              double *vv, double *vev, void *stream, int sync);
+
+int agf2_b200_moments_uhf_dev(const double *ixq_a, int64_t ld_ixq, const double *qja_a,
+                              int64_t ld_qja_a, const double *qja_b, int64_t ld_qja_b,
+                              const double *ei_a, const double *ei_b, const double *ea_a,
+                              const double *ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                              int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart,
+                              int64_t iend, double os_factor, double ss_factor, int64_t part,
+                              int64_t nparts, double *vv, double *vev, void *stream, int sync);
+
+/* Pole compression on the device (replaces auxgf/agf2/optragf2.py:270-278):
+ *   b = chol(vv)^T ; m = b^-T vev b^-1 ; (e, u) = eigh(m) ; c = b^T u
+ * vv, vev: (nphys, nphys) f64 symmetric.  e: (nphys), c: (nphys, nphys) row-major with
+ * c c^T = vv and c diag(e) c^T = vev.  `on_device` != 0: all four pointers are device memory. */
+int agf2_b200_compress(const double *vv, const double *vev, int64_t nphys, double *e, double *c,
+                       int on_device);
+
+/* Dense symmetric eigensolver (cuSOLVER dsyevd) for the extended Fock matrix
+ * (replaces np.linalg.eigh in auxgf/aux/eig.py:23-33).  a: (n, n) symmetric row-major, untouched;
+ * w: (n) ascending; v: (n, n) row-major with eigenvectors in COLUMNS (NumPy convention). */
+int agf2_b200_eigh(const double *a, int64_t n, double *w, double *v, int on_device);
+
+/* Instrumentation: number of kernels launched by this library since the last reset, and the
+ * device time (ms, CUDA events) of the last moments call's two kernels summed over launches. */
+int64_t agf2_b200_launch_count(int reset);
+int agf2_b200_last_kernel_ms(double *k1_form_ms, double *k2_moment_ms);
+
+/* Debug: route the moment build through the naive one-thread-per-element CUDA kernels (same
+ * planner, no tensor cores); used by the tests to separate planner bugs from kernel bugs. */
+int agf2_b200_set_simple_kernels(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGF2_B200_H */

@@ -1,0 +1,163 @@
+"""GPU parity tests: the CUDA moment build, called through the C-ABI (auxgf_b200.lib.agf2 ->
+libagf2_b200.so), against the oracle (oracle/agf2_oracle.py, pinned in tests/test_oracle.py) on the
+same seeded inputs, against the committed golden vectors of the reference's own C loop, and through
+size-independent properties.  Tolerance: moments within 1e-10 relative (BASELINE.json north_star)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import agf2_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from auxgf_b200.lib import agf2 as lib
+    return lib
+
+
+def _check_rhf(lib, o, v, n, p, seed, i0=0, i1=None, os_f=1.0, ss_f=1.0, tol=TOL):
+    i1 = o if i1 is None else i1
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, seed)
+    vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p, i0, i1, os_f, ss_f)
+    rv, rev = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, i0, i1, os_f, ss_f)
+    assert relerr(vv, rv) < tol and relerr(vev, rev) < tol, (relerr(vv, rv), relerr(vev, rev))
+    return vv, vev
+
+
+@pytest.mark.parametrize("simple", [True, False])
+def test_golden_rhf(lib, golden_dir, simple):
+    lib.set_simple_kernels(simple)
+    try:
+        for path in sorted(glob.glob(os.path.join(golden_dir, "rhf_*.npz"))):
+            g = np.load(path)
+            o, v, n, p, seed, i0, i1 = [int(x) for x in g["shape"]]
+            ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, seed)
+            vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p, i0, i1)
+            assert relerr(vv, g["vv"]) < TOL and relerr(vev, g["vev"]) < TOL, \
+                (path, simple, relerr(vv, g["vv"]), relerr(vev, g["vev"]))
+    finally:
+        lib.set_simple_kernels(False)
+
+
+@pytest.mark.parametrize("simple", [True, False])
+def test_golden_uhf(lib, golden_dir, simple):
+    lib.set_simple_kernels(simple)
+    try:
+        for path in sorted(glob.glob(os.path.join(golden_dir, "uhf_*.npz"))):
+            g = np.load(path)
+            oa, va, ob, vb, n, p, seed, i0, i1 = [int(x) for x in g["shape"]]
+            args = orc.synth_uhf(oa, va, ob, vb, n, p, seed)
+            vv, vev = lib.moments_uhf(*args, p, i0, i1)
+            assert relerr(vv, g["vv"]) < TOL and relerr(vev, g["vev"]) < TOL, \
+                (path, simple, relerr(vv, g["vv"]), relerr(vev, g["vev"]))
+    finally:
+        lib.set_simple_kernels(False)
+
+
+@pytest.mark.parametrize("shape", [
+    (5, 8, 40, 13), (3, 19, 37, 24), (12, 30, 100, 42), (7, 100, 130, 50), (6, 5, 16, 130),
+    (24, 240, 1000, 264), (40, 100, 333, 141), (9, 65, 129, 257), (2, 7, 15, 3),
+])
+def test_parity_ladder_rhf(lib, shape):
+    o, v, n, p = shape
+    _check_rhf(lib, o, v, n, p, seed=1)
+
+
+def test_reference_drop_in_symbols(lib):
+    """The void symbols with the reference's exact signature (optragf2.c:32-43, optuagf2.c:31-47)."""
+    o, v, n, p = 6, 21, 50, 30
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 4)
+    vv = np.full((p, p), 0.5); vev = np.full((p, p), -0.25)          # `+=` semantics
+    lib._libagf2.build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 1, 5, vv, vev)
+    rv, rev = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 1, 5)
+    assert relerr(vv - 0.5, rv) < TOL and relerr(vev + 0.25, rev) < TOL
+    a = orc.synth_uhf(5, 12, 4, 13, 40, 19, 6)
+    vv = np.zeros((19, 19)); vev = np.zeros((19, 19))
+    lib._libagf2.build_part_loop_uhf(*[np.ascontiguousarray(x) for x in a], 19, 5, 4, 12, 13, 40, 0, 5, vv, vev)
+    rv, rev = orc.np_build_part_loop_uhf(*a, 19, 5, 4, 12, 13, 40, 0, 5)
+    assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL
+
+
+def test_slices_rhf(lib):
+    o, v, n, p = 10, 33, 70, 45
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 2)
+    full = lib.moments_rhf(ixq, qja, ei, ea, p)
+    acc = [np.zeros((p, p)), np.zeros((p, p))]
+    for a, b in ((0, 3), (3, 4), (4, 10)):
+        part = _check_rhf(lib, o, v, n, p, 2, a, b)
+        acc[0] += part[0]; acc[1] += part[1]
+    assert relerr(acc[0], full[0]) < TOL and relerr(acc[1], full[1]) < TOL
+    assert relerr(full[0], full[0].T) < 1e-13     # full range: exactly symmetric by construction
+
+
+def test_scs_factors(lib):
+    _check_rhf(lib, 8, 20, 60, 31, seed=5, os_f=1.2, ss_f=1.0 / 3.0)
+    _check_rhf(lib, 8, 20, 60, 31, seed=5, i0=2, i1=6, os_f=1.2, ss_f=1.0 / 3.0)
+    _check_rhf(lib, 8, 20, 60, 31, seed=5, os_f=0.0, ss_f=1.0)
+    _check_rhf(lib, 8, 20, 60, 31, seed=5, os_f=1.0, ss_f=0.0)
+
+
+@pytest.mark.parametrize("shape", [(8, 84, 7, 85, 300, 92), (4, 9, 3, 10, 40, 13), (20, 40, 19, 41, 128, 60)])
+def test_parity_uhf(lib, shape):
+    oa, va, ob, vb, n, p = shape
+    args = orc.synth_uhf(oa, va, ob, vb, n, p, 3)
+    for (i0, i1, os_f, ss_f) in ((0, oa, 1.0, 1.0), (1, oa - 1, 1.0, 1.0), (0, oa, 1.2, 1.0 / 3.0)):
+        vv, vev = lib.moments_uhf(*args, p, i0, i1, os_f, ss_f)
+        rv, rev = orc.np_build_part_loop_uhf(*args, p, oa, ob, va, vb, n, i0, i1, os_f, ss_f)
+        assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL, (shape, i0, i1, relerr(vv, rv), relerr(vev, rev))
+
+
+def test_small_workspace_many_chunks(lib):
+    """Force many chunks (tiny workspace) -- exercises the chunk loop and tile double-buffering."""
+    lib.set_workspace_bytes(1 << 20)
+    try:
+        _check_rhf(lib, 12, 30, 100, 140, seed=8)
+        _check_rhf(lib, 12, 30, 100, 140, seed=8, i0=3, i1=9)
+    finally:
+        lib.set_workspace_bytes(40 << 20)
+
+
+def test_properties_medium(lib):
+    """Size-independent properties on a shape the NumPy oracle would need minutes for:
+    symmetry, PSD of vv, energy-shift identity  vev(e + d) - vev(e) = d * vv  (E = e_i+e_j-e_a is
+    linear in a uniform shift d of the occupied energies: shift of 2d - 0), and linearity in ixq."""
+    o, v, n, p = 48, 200, 1024, 400
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 9)
+    vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p)
+    assert relerr(vv, vv.T) < 1e-13 and relerr(vev, vev.T) < 1e-13
+    assert np.linalg.eigvalsh(vv).min() > 0
+    d = 0.37
+    vv2, vev2 = lib.moments_rhf(ixq, qja, ei + d, ea - d, p)      # E -> E + 3d
+    assert relerr(vv2, vv) < 1e-12
+    assert relerr(vev2 - vev, 3 * d * vv) < 1e-9
+    vv3, vev3 = lib.moments_rhf(2.0 * ixq, qja, ei, ea, p)          # quadratic in ixq
+    assert relerr(vv3, 4 * vv) < 1e-12 and relerr(vev3, 4 * vev) < 1e-12
+    # one slice of the same problem against the reference binary / NumPy oracle
+    r = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 5, 7)
+    g = lib.moments_rhf(ixq, qja, ei, ea, p, 5, 7)
+    assert relerr(g[0], r[0]) < TOL and relerr(g[1], r[1]) < TOL
+
+
+def test_compress_and_eigh(lib):
+    o, v, n, p = 12, 30, 100, 42
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 0)
+    vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p)
+    e, c = lib.compress(vv, vev)
+    assert relerr(c @ c.T, vv) < 1e-10 and relerr((c * e) @ c.T, vev) < 1e-10
+    e_ref, _ = orc.np_compress(vv, vev)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-9)
+    a = np.random.default_rng(0).standard_normal((97, 97)); a = a + a.T
+    w, u = lib.eigh(a)
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(a), rtol=0, atol=1e-11)
+    assert relerr((u * w) @ u.T, a) < 1e-12
+    with pytest.raises(lib.Agf2B200Error):
+        lib.compress(-np.eye(5), np.eye(5))      # not SPD -> status, like the reference's LinAlgError
