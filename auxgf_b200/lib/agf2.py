@@ -207,3 +207,79 @@ def eigh(a):
     w = np.empty(n); v = np.empty((n, n))
     check(_libagf2.agf2_b200_eigh(a.ctypes.data, n, w.ctypes.data, v.ctypes.data, 0))
     return w, v
+
+
+# ---- device-resident calls (torch tensors as containers only) ---------------------------------
+def _check_dev(t, name):
+    import torch
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous float64 CUDA tensor" % name)
+    return t
+
+
+def moments_rhf_dev(ixq, qja, ei, ea, istart=0, iend=None, os_factor=1.0, ss_factor=1.0, part=0, nparts=1,
+                    vv=None, vev=None, sync=True, naux=None):
+    """Device-resident moment build.  ixq: (nocc, nphys, ld>=naux), qja: (naux, nocc, ld>=nvir) CUDA f64
+    tensors whose last dimension may be padded to an even pitch (logical sizes: ``naux`` keyword,
+    ``ea.numel()``).  Returns (vv, vev) CUDA tensors (accumulated into when given)."""
+    import torch
+    _check_dev(ixq, "ixq"); _check_dev(qja, "qja"); _check_dev(ei, "ei"); _check_dev(ea, "ea")
+    nocc, nphys, ld_ixq = ixq.shape
+    naux = ld_ixq if naux is None else naux
+    ld_qja = qja.shape[2]
+    nvir = ea.numel()
+    assert qja.shape[0] == naux and qja.shape[1] == nocc and ei.numel() == nocc and ld_qja >= nvir
+    iend = nocc if iend is None else iend
+    if vv is None:
+        vv = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq.device)
+    if vev is None:
+        vev = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq.device)
+    stream = torch.cuda.current_stream(ixq.device).cuda_stream
+    check(_libagf2.agf2_b200_moments_rhf_dev(ixq.data_ptr(), ld_ixq, qja.data_ptr(), ld_qja, ei.data_ptr(),
+                                             ea.data_ptr(), nphys, nocc, nvir, naux, istart, iend, os_factor,
+                                             ss_factor, part, nparts, vv.data_ptr(), vev.data_ptr(), stream,
+                                             1 if sync else 0))
+    return vv, vev
+
+
+def moments_uhf_dev(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, istart=0, iend=None, os_factor=1.0,
+                    ss_factor=1.0, part=0, nparts=1, vv=None, vev=None, sync=True, naux=None):
+    import torch
+    for t, n in ((ixq_a, "ixq_a"), (qja_a, "qja_a"), (qja_b, "qja_b"), (ei_a, "ei_a"), (ei_b, "ei_b"),
+                 (ea_a, "ea_a"), (ea_b, "ea_b")):
+        _check_dev(t, n)
+    nocc_a, nphys, ld_ixq = ixq_a.shape
+    naux = ld_ixq if naux is None else naux
+    nocc_b, nvir_a, nvir_b = ei_b.numel(), ea_a.numel(), ea_b.numel()
+    iend = nocc_a if iend is None else iend
+    if vv is None:
+        vv = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq_a.device)
+    if vev is None:
+        vev = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq_a.device)
+    stream = torch.cuda.current_stream(ixq_a.device).cuda_stream
+    check(_libagf2.agf2_b200_moments_uhf_dev(ixq_a.data_ptr(), ld_ixq, qja_a.data_ptr(), qja_a.shape[2],
+                                             qja_b.data_ptr(), qja_b.shape[2], ei_a.data_ptr(), ei_b.data_ptr(),
+                                             ea_a.data_ptr(), ea_b.data_ptr(), nphys, nocc_a, nocc_b, nvir_a,
+                                             nvir_b, naux, istart, iend, os_factor, ss_factor, part, nparts,
+                                             vv.data_ptr(), vev.data_ptr(), stream, 1 if sync else 0))
+    return vv, vev
+
+
+def compress_dev(vv, vev):
+    import torch
+    n = vv.shape[0]
+    e = torch.empty(n, dtype=torch.float64, device=vv.device)
+    c = torch.empty((n, n), dtype=torch.float64, device=vv.device)
+    torch.cuda.current_stream(vv.device).synchronize()
+    check(_libagf2.agf2_b200_compress(vv.data_ptr(), vev.data_ptr(), n, e.data_ptr(), c.data_ptr(), 1))
+    return e, c
+
+
+def eigh_dev(a):
+    import torch
+    n = a.shape[0]
+    w = torch.empty(n, dtype=torch.float64, device=a.device)
+    v = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    torch.cuda.current_stream(a.device).synchronize()
+    check(_libagf2.agf2_b200_eigh(a.data_ptr(), n, w.data_ptr(), v.data_ptr(), 1))
+    return w, v

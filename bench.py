@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- DF-AGF2(None,0) self-energy moment build on B200 (BASELINE.json metric).
+
+A "step" is one full moment build of the synthetic shape (default S: nocc=100, nvir=1000, naux=4000,
+nphys=nocc+nvir=1100): the occupied-sector call  build_part_loop(o=nocc, v=nvir)  plus the
+virtual-sector call  build_part_loop(o=nvir, v=nocc)  (= one ``OptRAGF2.build()``,
+auxgf/agf2/optragf2.py:283-293), F_alg = 1.50e15 flop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--shape nocc,nvir,naux,nphys] [--no-e2e] [--no-cpu]
+
+  value    : seconds per moment build with the DF tensors already resident in HBM (device C-ABI)
+  e2e      : the same build through the reference-facing host-pointer C-ABI
+             (agf2_b200_build_part_loop_rhf: host ixq/qja in, host vv/vev out, copies in the timed region)
+  roofline : dominant kernel k1_form (integral formation), algorithmic FP64 flop / summed launch time
+             measured with CUDA events, against the cuBLAS DGEMM peak measured on this pool's B200
+             (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json carries no FP64 figure)
+  cpu_baseline / --impl reference : the reference's own C loop (oracle/_ref/agf2.so, built from
+             /root/reference/auxgf/lib/libagf2) on the host cores, on a bounded slice of poles,
+             scaled to one build.
+N > 1 (torchrun): pair-work items are dealt round-robin to the ranks (part/nparts of the C-ABI), one
+NCCL all-reduce of [vv|vev] per sector; total work is fixed -> "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DGEMM_PEAK_FALLBACK = 35.9   # TFLOP/s, cublasDgemm 8192^3 on this pool (profiles/fp64_peak_r01.json)
+
+
+def f_alg(o, v, n, p):
+    return 2.0 * p * o * o * v * n + 4.0 * p * p * o * o * v
+
+
+def f_k1(o, v, n, p):
+    return 2.0 * p * o * o * v * n
+
+
+def fp64_peak():
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")) as f:
+            return float(json.load(f)["dgemm_tflops_sustained"]), "measured cublasDgemm 8192^3 (profiles/fp64_peak_r01.json)"
+    except Exception:
+        return DGEMM_PEAK_FALLBACK, "fallback constant (profiles/fp64_peak_r01.json unreadable)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference leg (oracle/_ref = the reference's own C loop; else the NumPy port)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(o, v, n, p, budget_s=20.0):
+    """Times the reference loop on a slice of occupied poles of the occupied-sector call and scales by
+    executed work to one full build (work per pole is identical in both sectors: 4PovN + 8P^2ov)."""
+    from oracle import agf2_oracle as orc
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    # scratch of the reference is 3*P*o*v doubles per OpenMP thread (optragf2.c:105-107)
+    per_thread_gb = 3.0 * p * o * v * 8 / 1e9
+    ixq = (rng.standard_normal((o * p, n), dtype=np.float32) / np.sqrt(n)).astype(np.float64)
+    qja = (rng.standard_normal((n, o * v), dtype=np.float32) / np.sqrt(n)).astype(np.float64)
+    ei = np.sort(rng.uniform(-2.0, -0.5, o)); ea = np.sort(rng.uniform(0.5, 3.0, v))
+    if orc.have_ref():
+        kind = "reference"
+        orc.load_ref()
+        omp = int(max(1, min(cores, 24.0 // max(per_thread_gb, 1e-9), o)))
+        blas = max(1, cores // omp)
+        orc.ref_set_threads(omp=omp, blas=blas)
+        fn = lambda i0, i1: orc.ref_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, i0, i1)  # noqa: E731
+        threads = omp * blas
+    else:
+        kind = "port"
+        omp, blas, threads = 1, cores, cores
+        fn = lambda i0, i1: orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, i0, i1)  # noqa: E731
+    t0 = time.perf_counter(); fn(0, omp); t1 = time.perf_counter() - t0        # warm + calibrate
+    ni = int(max(omp, min(o, omp * max(1, int(budget_s / max(t1, 1e-3))))))
+    t0 = time.perf_counter(); fn(0, ni); dt = time.perf_counter() - t0
+    per_pole = dt / ni
+    build_s = per_pole * (o + v)          # o poles in the occupied sector + v poles in the virtual one
+    return {"value": build_s, "unit": "s", "cores": threads, "kind": kind,
+            "sample": "poles [0,%d) of the occupied-sector call (o=%d,v=%d,naux=%d,nphys=%d) in %.1f s, "
+                      "OMP=%d x BLAS=%d threads, scaled by (nocc+nvir)/%d poles (equal work per pole in both sectors)"
+                      % (ni, o, v, n, p, dt, omp, blas, ni),
+            "tflops_executed": 2.0 * f_alg(o, v, n, p) / o * ni / dt * 1e-12,
+            "tflops_algorithmic": (f_alg(o, v, n, p) + f_alg(v, o, n, p)) / build_s * 1e-12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default="100,1000,4000,1100")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    o, v, n, p = [int(x) for x in args.shape.split(",")]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "synthetic DF shape nocc=%d nvir=%d naux=%d nphys=%d: occupied + virtual sector moment build" % (o, v, n, p)
+    flops_build = f_alg(o, v, n, p) + f_alg(v, o, n, p)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        cb = None
+        for _ in range(max(1, args.warmup > 0) + args.steps):
+            cb = cpu_reference_sample(o, v, n, p, budget_s=args.cpu_budget)
+            vals.append(cb["value"])
+        val = float(np.mean(vals[-args.steps:]))
+        cb["value"] = val
+        print(json.dumps({
+            "impl": "reference", "metric": "agf2_moment_build_seconds_per_iter", "value": val, "unit": "s",
+            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload}, "tflops": flops_build / val * 1e-12, "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    from auxgf_b200.lib import agf2 as lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def make(sh, scale, seed):
+        g = torch.Generator(device=dev); g.manual_seed(seed)
+        return torch.randn(sh, generator=g, device=dev, dtype=torch.float64) * scale
+
+    sc = 1.0 / np.sqrt(n)
+    # occupied-sector call: o "occupied" poles, v "virtual"; virtual-sector call: roles swapped
+    ixq_o = make((o, p, n), sc, 1); qja_o = make((n, o, v), sc, 2)
+    ixq_v = make((v, p, n), sc, 3); qja_v = make((n, v, o), sc, 4)
+    e_o = torch.sort(torch.rand(o, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
+    e_v = torch.sort(torch.rand(v, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
+    out = torch.zeros((2, 2, p, p), device=dev, dtype=torch.float64)   # [sector][vv|vev]
+
+    def step():
+        out.zero_()
+        lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, vv=out[0, 0], vev=out[0, 1], sync=False)
+        lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, vv=out[1, 0], vev=out[1, 1], sync=False)
+        if world > 1:
+            dist.all_reduce(out)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    lib.launch_count(reset=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_ms = k2_ms = 0.0
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.launch_count()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    checksum = float(out.sum().item())
+
+    # per-kernel device time of one more (untimed) step, per-launch CUDA events inside the library
+    lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, sync=True)
+    a1, b1 = lib.last_kernel_ms()
+    lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, sync=True)
+    a2, b2 = lib.last_kernel_ms()
+    k1_ms, k2_ms = a1 + a2, b1 + b2
+
+    # ------------------------------------------------------------------ e2e (host buffers, rank 0, N=1)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        host_gb = (ixq_o.numel() + qja_o.numel() + ixq_v.numel() + qja_v.numel()) * 8 / 1e9
+        try:
+            avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 1e9
+        except Exception:
+            avail_gb = 0.0
+        if avail_gb > host_gb * 1.3 + 8:
+            h = [ixq_o.cpu().numpy().reshape(o * p, n), qja_o.cpu().numpy().reshape(n, o * v),
+                 ixq_v.cpu().numpy().reshape(v * p, n), qja_v.cpu().numpy().reshape(n, v * o)]
+            eo_h, ev_h = e_o.cpu().numpy(), e_v.cpu().numpy()
+            del ixq_o, qja_o, ixq_v, qja_v
+            torch.cuda.empty_cache()
+
+            def host_step():
+                r0 = lib.moments_rhf(h[0], h[1], eo_h, ev_h, p)
+                r1 = lib.moments_rhf(h[2], h[3], ev_h, eo_h, p)
+                return r0, r1
+            host_step()
+            t0 = time.perf_counter()
+            for _ in range(max(1, min(args.steps, 2))):
+                res = host_step()
+            dt = (time.perf_counter() - t0) / max(1, min(args.steps, 2))
+            chk2 = float(sum(a.sum() for r in res for a in r))
+            e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v),
+                   "d2h_bytes_per_step": 4 * p * p * 8, "tflops": flops_build / dt * 1e-12,
+                   "checksum_rel_diff_vs_device_path": abs(chk2 - checksum) / max(abs(checksum), 1e-300),
+                   "api": "agf2_b200_build_part_loop_rhf (host pointers, pageable NumPy buffers)"}
+        else:
+            e2e = {"value": None, "unit": "s", "skipped": "host RAM %.0f GB < %.0f GB needed for the host copies" % (avail_gb, host_gb * 1.3 + 8)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = fp64_peak()
+    k1_flops = f_k1(o, v, n, p) + f_k1(v, o, n, p)
+    k1_tf = k1_flops / world / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else None
+    k2_flops = flops_build - k1_flops
+    line = {
+        "metric": "agf2_moment_build_seconds_per_iter", "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "l2": "inputs (%.1f GB) exceed the 126 MB L2" % ((o * p * n + n * o * v) * 2 * 8 / 1e9),
+                   "parallelism": "pair items round-robin over %d GPU(s) + 1 NCCL all-reduce" % world},
+        "tflops": flops_build / (ms_per_step * 1e-3) * 1e-12,
+        "frac_of_fp64_peak": flops_build / (ms_per_step * 1e-3) * 1e-12 / (peak * world),
+        "fp64_peak_tflops": peak, "fp64_peak_source": peak_src,
+        "roofline": {"bound": "tensor", "kernel": "k1_form (FP64 DMMA.8x8x4)", "achieved": k1_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": (k1_tf / peak) if k1_tf else None, "traffic": None,
+                     "k1_ms_per_step": k1_ms, "k2_ms_per_step": k2_ms,
+                     "k2_achieved": k2_flops / world / (k2_ms * 1e-3) * 1e-12 if k2_ms > 0 else None},
+        "gpu_launches": int(launches), "clocks": clocks, "checksum": checksum,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_reference_sample(o, v, n, p, budget_s=args.cpu_budget)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
