@@ -74,6 +74,7 @@ struct Ctx {
     size_t stage_elems[8] = {0};
     // instrumentation
     int64_t launches = 0;
+    int64_t chunk_counter = 0;
     std::vector<EventPair> events;
     size_t events_used = 0;
     double last_ms[2] = {0, 0};
@@ -263,7 +264,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     CU_TRY(cudaStreamSynchronize(st));   // t2 vectors are pageable host memory
 
     c.events_used = 0;
-    int chunk_idx = 0;
+    int64_t& chunk_idx = c.chunk_counter;   // global: tile staging buffers alternate across calls too
     std::vector<K1Tile> tiles;
     std::vector<SubTile> plain;
 
@@ -320,9 +321,11 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             if (col == 0) return fail(AGF2_B200_EINVAL, "workspace too small for one work item");
             // two independent plain blocks share one CTA tile
             std::stable_sort(plain.begin(), plain.end(), [](const SubTile& a, const SubTile& b) { return a.nb > b.nb; });
-            for (size_t k = 0; k < plain.size(); k += 2) {
+            for (size_t k = 0; k < plain.size();) {
                 const SubTile& s1 = plain[k];
-                const SubTile* s2 = k + 1 < plain.size() ? &plain[k + 1] : nullptr;
+                // only equal-width blocks share a CTA tile: k1_form is instantiated for (n, n) and (n, 0)
+                const SubTile* s2 = (k + 1 < plain.size() && plain[k + 1].nb == s1.nb) ? &plain[k + 1] : nullptr;
+                k += s2 ? 2 : 1;
                 for (int xb = 0; xb < nxb; ++xb) {
                     K1Tile t;
                     memset(&t, 0, sizeof(t));
@@ -341,7 +344,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                              [](const K1Tile& a, const K1Tile& b) { return a.nb1 + a.nb2 > b.nb1 + b.nb2; });
 
             // ---- upload the tile list (double-buffered pinned staging) ----
-            const int buf = chunk_idx & 1;
+            const int buf = (int)(chunk_idx & 1);
             if (tiles.size() > c.t1_cap) {
                 CU_TRY(cudaStreamSynchronize(st));
                 for (int b = 0; b < 2; ++b) {
@@ -356,7 +359,8 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                     CU_TRY(cudaMallocHost(&c.h_t1[b], cap * sizeof(K1Tile)));
                 }
                 c.t1_cap = cap;
-            } else if (chunk_idx >= 2) {
+            } else {
+                // the previous user of this staging buffer (possibly an earlier, still running call)
                 CU_TRY(cudaEventSynchronize(c.t1_free[buf]));
             }
             memcpy(c.h_t1[buf], tiles.data(), tiles.size() * sizeof(K1Tile));

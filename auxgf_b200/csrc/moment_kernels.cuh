@@ -25,7 +25,10 @@ constexpr int kTileM = 128;        // rows (x) per CTA tile
 constexpr int kTileN = 64;         // max columns per integral block / moment tile
 constexpr int kKB = 16;            // K elements per pipeline stage (128 B rows -> SWIZZLE_128B)
 constexpr int kConsumerWarps = 8;  // each owns 16 rows x 64 cols
-constexpr int kThreads = (kConsumerWarps + 1) * 32;  // + 1 TMA producer warp
+// 8 warps = 2 per SM sub-partition -> up to 255 registers per thread.  (A ninth, dedicated TMA warp would
+// put 3 warps on one sub-partition and cap every thread at 168 registers.)  Lane 0 of warp 0 issues the
+// TMA loads kStages-2 iterations ahead, into the stage all warps released two iterations ago.
+constexpr int kThreads = kConsumerWarps * 32;
 
 // ---- K1 ---------------------------------------------------------------------------------------
 struct K1Tile {
@@ -48,6 +51,91 @@ constexpr int kK1SmemBytes = kK1Stages * kK1StageBytes + 1024 /*align slack*/ + 
 // pi: logical fragment row -> physical row inside an 8-row group, chosen so that the two rows read
 // by one quarter-warp (LDS.128) fall into different halves of the 128B swizzle atom.
 __device__ __forceinline__ int pi8(int g) { return (g >> 1) | ((g & 1) << 2); }
+
+
+// Main loop of k1_form for compile-time block widths (NB1, NB2 in units of 8 columns).
+// One pipeline stage (16 Q) = 8 "units" (ks, e, set): the fragments of unit u+1 are loaded while the
+// DMMAs of unit u issue (they belong to the other block, so the registers are free), including across
+// the stage boundary, so shared-memory latency never sits between dependent instructions.
+template <int NB1, int NB2, typename Producer>
+__device__ __forceinline__ void k1_mainloop(const uint8_t* __restrict__ gbase, uint32_t bar_full, uint32_t bar_empty,
+                                            int nk, int warp, int lane, double (&acc1)[2][8][2],
+                                            double (&acc2)[2][8][2], Producer& produce)
+{
+    const int gid = lane >> 2, tig = lane & 3;
+    const int pg = pi8(gid);
+    // A-type (K-contiguous rows, LDS.128): row = 16*warp + 8*mb + pg, chunk = 4*ks + tig
+    const uint32_t a_row = (uint32_t)((16 * warp + pg) * 128);
+    const uint32_t a_off[2] = {a_row + (uint32_t)(((tig) ^ pg) << 4), a_row + (uint32_t)(((4 + tig) ^ pg) << 4)};
+    // B-type (rows = Q, 16 columns per 2 KB box, LDS.64): row = 8*ks + 2*tig + e,
+    // column-in-box = 8*(nb&1) + gid  ->  chunk = 4*(nb&1) + gid/2, half = gid&1
+    uint32_t b_off[2][2];
+#pragma unroll
+    for (int par = 0; par < 2; ++par)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int r = 2 * tig + e;
+            const int chunk = 4 * par + (gid >> 1);
+            b_off[par][e] = (uint32_t)(r * 128 + ((chunk ^ r) << 4) + (gid & 1) * 8);
+        }
+
+    double2 fa[2][2];   // [set][mb]: A fragments of the current ks (x: e = 0, y: e = 1)
+    double fb[2][8];    // [set][nb]: B fragments of the current (ks, e)
+    constexpr bool kDual = NB2 > 0;
+    constexpr int kUnits = kDual ? 8 : 4;
+
+    auto load_unit = [&](const uint8_t* st, int u) {
+        const int set = kDual ? (u & 1) : 0;
+        const int e = kDual ? ((u >> 1) & 1) : (u & 1);
+        const int ks = kDual ? (u >> 2) : (u >> 1);
+        if (e == 0) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+                fa[set][mb] = *reinterpret_cast<const double2*>(st + set * 16384 + a_off[ks] + mb * 1024);
+        }
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            if (nb < (set ? NB2 : NB1))
+                fb[set][nb] = *reinterpret_cast<const double*>(st + 32768 + set * 8192 + b_off[nb & 1][e] +
+                                                               (nb >> 1) * 2048 + ks * 1024);
+    };
+    auto compute_unit = [&](int u) {
+        const int set = kDual ? (u & 1) : 0;
+        const int e = kDual ? ((u >> 1) & 1) : (u & 1);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+            if (nb < (set ? NB2 : NB1)) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const double a = e ? fa[set][mb].y : fa[set][mb].x;
+                    if (set) dmma884(acc2[mb][nb][0], acc2[mb][nb][1], a, fb[1][nb]);
+                    else dmma884(acc1[mb][nb][0], acc1[mb][nb][1], a, fb[0][nb]);
+                }
+            }
+    };
+
+    mbar_wait(bar_full, 0);
+    load_unit(gbase, 0);
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % kK1Stages;
+        const uint8_t* st = gbase + s * kK1StageBytes;
+        if (warp == 0 && lane == 0) produce(it + kK1Stages - 2);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kUnits; ++u) {
+            if (u + 1 < kUnits) {
+                load_unit(st, u + 1);
+            } else if (it + 1 < nk) {
+                const int s2 = (it + 1) % kK1Stages;
+                mbar_wait(bar_full + 8 * s2, ((it + 1) / kK1Stages) & 1);
+                load_unit(gbase + s2 * kK1StageBytes, 0);
+            }
+            compute_unit(u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
@@ -76,53 +164,35 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            tma_prefetch_desc(&mapA);
-            tma_prefetch_desc(t.bsel1 ? &mapB1 : &mapB0);
-            const int ng1 = (t.nb1 + 1) >> 1, ng2 = (t.nb2 + 1) >> 1;   // 16-column TMA boxes
-            const uint32_t bytes = (uint32_t)((t.nb1 ? kTileM * kKB * 8 : 0) + (t.nb2 ? kTileM * kKB * 8 : 0) +
-                                              (ng1 + ng2) * 16 * kKB * 8);
-            const CUtensorMap* mB1 = t.bsel1 ? &mapB1 : &mapB0;
-            const CUtensorMap* mB2 = t.bsel2 ? &mapB1 : &mapB0;
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % kK1Stages;
-                if (it >= kK1Stages) mbar_wait(bar_empty + 8 * s, ((it / kK1Stages) - 1) & 1);
-                const uint32_t st = base + s * kK1StageBytes;
-                const uint32_t fb = bar_full + 8 * s;
-                mbar_expect_tx(fb, bytes);
-                const int q0 = it * kKB;
-                if (t.nb1) tma_load_3d(st, &mapA, q0, t.xb * kTileM, t.i1, fb);
-                if (t.nb2) tma_load_3d(st + 16384, &mapA, q0, t.xb * kTileM, t.i2, fb);
-                for (int g = 0; g < ng1; ++g)
-                    tma_load_3d(st + 32768 + g * 2048, mB1, t.a1 + 16 * g, t.j1, q0, fb);
-                for (int g = 0; g < ng2; ++g)
-                    tma_load_3d(st + 40960 + g * 2048, mB2, t.a2 + 16 * g, t.j2, q0, fb);
-            }
-        }
-        return;
+    // ===== TMA producer (executed by lane 0 of warp 0): loads of pipeline iteration j =====
+    const int ng1 = (t.nb1 + 1) >> 1, ng2 = (t.nb2 + 1) >> 1;   // 16-column TMA boxes
+    const uint32_t stage_tx = (uint32_t)((t.nb1 ? kTileM * kKB * 8 : 0) + (t.nb2 ? kTileM * kKB * 8 : 0) +
+                                         (ng1 + ng2) * 16 * kKB * 8);
+    auto produce = [&](int j) {
+        if (j >= nk) return;
+        const int s = j % kK1Stages;
+        if (j >= kK1Stages) mbar_wait(bar_empty + 8 * s, ((j / kK1Stages) - 1) & 1);
+        const uint32_t st = base + s * kK1StageBytes;
+        const uint32_t fb = bar_full + 8 * s;
+        const CUtensorMap* mB1 = t.bsel1 ? &mapB1 : &mapB0;
+        const CUtensorMap* mB2 = t.bsel2 ? &mapB1 : &mapB0;
+        mbar_expect_tx(fb, stage_tx);
+        const int q0 = j * kKB;
+        if (t.nb1) tma_load_3d(st, &mapA, q0, t.xb * kTileM, t.i1, fb);
+        if (t.nb2) tma_load_3d(st + 16384, &mapA, q0, t.xb * kTileM, t.i2, fb);
+        for (int g = 0; g < ng1; ++g) tma_load_3d(st + 32768 + g * 2048, mB1, t.a1 + 16 * g, t.j1, q0, fb);
+        for (int g = 0; g < ng2; ++g) tma_load_3d(st + 40960 + g * 2048, mB2, t.a2 + 16 * g, t.j2, q0, fb);
+    };
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(t.bsel1 ? &mapB1 : &mapB0);
+        for (int j = 0; j < kK1Stages - 2; ++j) produce(j);
     }
+    __syncwarp();
 
     // ===== consumers: 8 warps x (16 rows x 64 cols x 2 blocks) =====
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
-    // A-type (K-contiguous rows, LDS.128): row = 16*warp + 8*mb + pg, chunk = 4*s + tig
-    const uint32_t a_row = (uint32_t)((16 * warp + pg) * 128);
-    const uint32_t a_off0 = a_row + (uint32_t)(((tig) ^ pg) << 4);
-    const uint32_t a_off1 = a_row + (uint32_t)(((4 + tig) ^ pg) << 4);
-    // B-type (rows = Q, 16 columns per 2 KB box, LDS.64): row = 8*s + 2*tig + e,
-    // column-in-box = 8*(nb&1) + gid  ->  chunk = 4*(nb&1) + gid/2, half = gid&1
-    uint32_t b_off[2][2];
-#pragma unroll
-    for (int par = 0; par < 2; ++par)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int r = 2 * tig + e;
-            const int chunk = 4 * par + (gid >> 1);
-            b_off[par][e] = (uint32_t)(r * 128 + ((chunk ^ r) << 4) + (gid & 1) * 8);
-        }
-
     double acc1[2][8][2], acc2[2][8][2];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
@@ -131,43 +201,15 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
             acc1[mb][nb][0] = acc1[mb][nb][1] = 0.0;
             acc2[mb][nb][0] = acc2[mb][nb][1] = 0.0;
         }
-
     const int nb1 = t.nb1, nb2 = t.nb2;
-    for (int it = 0; it < nk; ++it) {
-        const int s = it % kK1Stages;
-        mbar_wait(bar_full + 8 * s, (it / kK1Stages) & 1);
-        const uint8_t* st = gbase + s * kK1StageBytes;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t ao = ks ? a_off1 : a_off0;
-            double2 fa1[2], fa2[2];
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                fa1[mb] = *reinterpret_cast<const double2*>(st + ao + mb * 1024);
-                fa2[mb] = *reinterpret_cast<const double2*>(st + 16384 + ao + mb * 1024);
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-#pragma unroll
-                for (int nb = 0; nb < 8; ++nb) {
-                    const uint32_t bo = b_off[nb & 1][e] + (uint32_t)((nb >> 1) * 2048 + ks * 1024);
-                    if (nb < nb1) {
-                        const double b = *reinterpret_cast<const double*>(st + 32768 + bo);
-#pragma unroll
-                        for (int mb = 0; mb < 2; ++mb)
-                            dmma884(acc1[mb][nb][0], acc1[mb][nb][1], e ? fa1[mb].y : fa1[mb].x, b);
-                    }
-                    if (nb < nb2) {
-                        const double b = *reinterpret_cast<const double*>(st + 40960 + bo);
-#pragma unroll
-                        for (int mb = 0; mb < 2; ++mb)
-                            dmma884(acc2[mb][nb][0], acc2[mb][nb][1], e ? fa2[mb].y : fa2[mb].x, b);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    switch (nb1 * 16 + nb2) {
+#define AGF2_K1_CASE(A, B) case (A) * 16 + (B): k1_mainloop<A, B>(gbase, bar_full, bar_empty, nk, warp, lane, acc1, acc2, produce); break;
+        AGF2_K1_CASE(8, 8) AGF2_K1_CASE(7, 7) AGF2_K1_CASE(6, 6) AGF2_K1_CASE(5, 5)
+        AGF2_K1_CASE(4, 4) AGF2_K1_CASE(3, 3) AGF2_K1_CASE(2, 2) AGF2_K1_CASE(1, 1)
+        AGF2_K1_CASE(8, 0) AGF2_K1_CASE(7, 0) AGF2_K1_CASE(6, 0) AGF2_K1_CASE(5, 0)
+        AGF2_K1_CASE(4, 0) AGF2_K1_CASE(3, 0) AGF2_K1_CASE(2, 0) AGF2_K1_CASE(1, 0)
+#undef AGF2_K1_CASE
+        default: __trap();   // the planner only emits (n, n) and (n, 0) tiles
     }
 
     // ===== fused epilogue: exchange combination + scaling, write W (never the raw integrals) =====
@@ -256,30 +298,31 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
     __syncthreads();
     if (nk <= 0) return;
 
-    if (warp == kConsumerWarps) {
-        if (lane == 0) {
-            tma_prefetch_desc(&mapWA);
-            tma_prefetch_desc(&mapWB);
-            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8;
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % kK2Stages;
-                if (it >= kK2Stages) mbar_wait(bar_empty + 8 * s, ((it / kK2Stages) - 1) & 1);
-                const uint32_t st = base + s * kK2StageBytes;
-                const uint32_t fb = bar_full + 8 * s;
-                mbar_expect_tx(fb, bytes);
-                const int k0 = (it0 + it) * kKB;
-                tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
-                tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
-                tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
-                bulk_load_1d(st + 24576, E + k0, kKB * 8, fb);
-            }
-        }
-        return;
+    // ===== TMA producer (lane 0 of warp 0) =====
+    auto produce = [&](int j) {
+        if (j >= nk) return;
+        constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8;
+        const int s = j % kK2Stages;
+        if (j >= kK2Stages) mbar_wait(bar_empty + 8 * s, ((j / kK2Stages) - 1) & 1);
+        const uint32_t st = base + s * kK2StageBytes;
+        const uint32_t fb = bar_full + 8 * s;
+        mbar_expect_tx(fb, bytes);
+        const int k0 = (it0 + j) * kKB;
+        tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
+        tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
+        tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
+        bulk_load_1d(st + 24576, E + k0, kKB * 8, fb);
+    };
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapWA);
+        tma_prefetch_desc(&mapWB);
+        for (int j = 0; j < kK2Stages - 2; ++j) produce(j);
     }
+    __syncwarp();
 
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
-    const uint32_t sw0 = (uint32_t)(((tig) ^ pg) << 4), sw1 = (uint32_t)(((4 + tig) ^ pg) << 4);
+    const uint32_t sw[2] = {(uint32_t)(((tig) ^ pg) << 4), (uint32_t)(((4 + tig) ^ pg) << 4)};
     const uint32_t a_row = (uint32_t)((16 * warp + pg) * 128);
     const uint32_t b_row = (uint32_t)(pg * 128);
 
@@ -292,35 +335,59 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
             cvev[mb][nb][0] = cvev[mb][nb][1] = 0.0;
         }
 
-    for (int it = 0; it < nk; ++it) {
-        const int s = it % kK2Stages;
-        mbar_wait(bar_full + 8 * s, (it / kK2Stages) & 1);
-        const uint8_t* st = gbase + s * kK2StageBytes;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t sw = ks ? sw1 : sw0;
+    // One stage = 4 units (ks, half): unit u+1's fragments are loaded while unit u's 32 DMMAs issue.
+    double2 fa[2][2], fe[2][2];   // [ks parity][mb]: A fragments and their energy-weighted copies
+    double2 fb[2][4];             // [half][j]: B fragments of n-blocks 4*half + j
+    auto load_unit = [&](const uint8_t* st, int u) {
+        const int ks = u >> 1, half = u & 1;
+        if (half == 0) {
             const double2 ev = *reinterpret_cast<const double2*>(st + 24576 + (4 * ks + tig) * 16);
-            double2 fa[2], fe[2];
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-                fa[mb] = *reinterpret_cast<const double2*>(st + a_row + mb * 1024 + sw);
-                fe[mb].x = fa[mb].x * ev.x;
-                fe[mb].y = fa[mb].y * ev.y;
+                fa[ks][mb] = *reinterpret_cast<const double2*>(st + a_row + mb * 1024 + sw[ks]);
+                fe[ks][mb].x = fa[ks][mb].x * ev.x;
+                fe[ks][mb].y = fa[ks][mb].y * ev.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            fb[half][j] = *reinterpret_cast<const double2*>(st + 16384 + b_row + (4 * half + j) * 1024 + sw[ks]);
+    };
+    auto compute_unit = [&](int u) {
+        const int ks = u >> 1, half = u & 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nb = 4 * half + j;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].x, fb[half][j].x);
+                dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].x, fb[half][j].x);
             }
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb) {
-                const double2 fb = *reinterpret_cast<const double2*>(st + 16384 + b_row + nb * 1024 + sw);
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[mb].x, fb.x);
-                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[mb].x, fb.x);
-                }
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[mb].y, fb.y);
-                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[mb].y, fb.y);
-                }
+            for (int mb = 0; mb < 2; ++mb) {
+                dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].y, fb[half][j].y);
+                dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].y, fb[half][j].y);
             }
+        }
+    };
+
+    mbar_wait(bar_full, 0);
+    load_unit(gbase, 0);
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % kK2Stages;
+        const uint8_t* st = gbase + s * kK2StageBytes;
+        if (warp == 0 && lane == 0) produce(it + kK2Stages - 2);
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < 3) {
+                load_unit(st, u + 1);
+            } else if (it + 1 < nk) {
+                const int s2 = (it + 1) % kK2Stages;
+                mbar_wait(bar_full + 8 * s2, ((it + 1) / kK2Stages) & 1);
+                load_unit(gbase + s2 * kK2StageBytes, 0);
+            }
+            compute_unit(u);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
