@@ -388,8 +388,9 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             const std::vector<K2Tile>& t2 = sym ? t2_sym : t2_all;
             const K2Tile* d_t2 = sym ? c.d_t2 : c.d_t2 + t2_sym.size();
             const int nk2 = (int)((col + kKB - 1) / kKB);
-            int nsplit = (int)((2 * c.num_sms + (int)t2.size() - 1) / (int)t2.size());
-            nsplit = std::max(1, std::min(nsplit, std::max(1, nk2 / 8)));
+            // stream-K grid: one CTA per SM, unless the chunk is too small to give each >= 8 iterations
+            const long long total_it = (long long)t2.size() * nk2;
+            const int grid2 = (int)std::max<long long>(1, std::min<long long>(c.num_sms, total_it / 8));
             record(st, 1, true);
             if (!c.simple) {
                 CUtensorMap mapWA, mapWB;
@@ -398,9 +399,8 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                 cuuint32_t b[2] = {kKB, 64};
                 if (int r = make_map(&mapWA, c.W[0], 2, d, s, b)) return r;
                 if (int r = make_map(&mapWB, sym ? c.W[0] : c.W[1], 2, d, s, b)) return r;
-                dim3 grid((unsigned)t2.size(), (unsigned)nsplit);
-                k2_moment<<<grid, kThreads, kK2SmemBytes, st>>>(mapWA, mapWB, c.E, d_t2, sym ? S_vv : A_vv,
-                                                               sym ? S_vev : A_vev, p_pad, nk2, nsplit);
+                k2_moment<<<grid2, kThreads, kK2SmemBytes, st>>>(mapWA, mapWB, c.E, d_t2, sym ? S_vv : A_vv,
+                                                                sym ? S_vev : A_vev, p_pad, nk2, (int)t2.size());
             } else {
                 k2_moment_simple<<<(unsigned)t2.size(), 256, 0, st>>>(c.W[0], sym ? c.W[0] : c.W[1], ldw, c.E, (int)col,
                                                                       d_t2, sym ? S_vv : A_vv, sym ? S_vev : A_vev, p_pad);

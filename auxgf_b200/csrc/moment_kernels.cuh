@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUtensorMap mapWB,
           const double* __restrict__ E, const K2Tile* __restrict__ tiles,
           double* __restrict__ acc_vv, double* __restrict__ acc_vev, long long ldacc,
-          int nk_total, int nsplit)
+          int nk_total, int ntiles)
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -281,11 +281,13 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
     const uint32_t bar_empty = bar_full + 8 * kK2Stages;
     uint8_t* const gbase = smem_raw + (base - smem_u32(smem_raw));
 
-    const K2Tile t = tiles[blockIdx.x];
-    const int split = blockIdx.y;
-    const int it0 = (int)(((long long)nk_total * split) / nsplit);
-    const int it1 = (int)(((long long)nk_total * (split + 1)) / nsplit);
-    const int nk = it1 - it0;
+    // stream-K: the (tile, k-iteration) space is linearised tile-major and cut into gridDim.x equal
+    // ranges, so every SM gets the same number of DMMA iterations whatever the tile count; a CTA
+    // flushes its accumulators (red.global.add) whenever its range crosses a tile boundary.
+    const long long total = (long long)ntiles * nk_total;
+    const long long L0 = total * blockIdx.x / gridDim.x;
+    const long long L1 = total * (blockIdx.x + 1) / gridDim.x;
+    const int nk = (int)(L1 - L0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -307,7 +309,9 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
         const uint32_t st = base + s * kK2StageBytes;
         const uint32_t fb = bar_full + 8 * s;
         mbar_expect_tx(fb, bytes);
-        const int k0 = (it0 + j) * kKB;
+        const long long L = L0 + j;
+        const K2Tile t = tiles[L / nk_total];
+        const int k0 = (int)(L % nk_total) * kKB;
         tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
         tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
         tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
@@ -371,6 +375,7 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
         }
     };
 
+    int tile = (int)(L0 / nk_total), kit = (int)(L0 % nk_total);
     mbar_wait(bar_full, 0);
     load_unit(gbase, 0);
     for (int it = 0; it < nk; ++it) {
@@ -391,22 +396,28 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-    }
-
-    // split-K / cross-chunk reduction: warp-level fragments straight into the global accumulators
-    const long long x0 = (long long)t.xb * kTileM + 16 * warp;
-    const long long y0 = (long long)t.yb * kTileN;
+        if (++kit == nk_total || it + 1 == nk) {
+            // split-K / cross-chunk reduction: warp-level fragments straight into the global accumulators
+            const K2Tile t = tiles[tile];
+            const long long x0 = (long long)t.xb * kTileM + 16 * warp;
+            const long long y0 = (long long)t.yb * kTileN;
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb) {
-        const long long row = x0 + 8 * mb + pg;
+            for (int mb = 0; mb < 2; ++mb) {
+                const long long row = x0 + 8 * mb + pg;
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb)
+                for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const long long col = y0 + 8 * nb + pi8(2 * tig + h);
-                red_add_f64(acc_vv + row * ldacc + col, cvv[mb][nb][h]);
-                red_add_f64(acc_vev + row * ldacc + col, cvev[mb][nb][h]);
+                    for (int h = 0; h < 2; ++h) {
+                        const long long col = y0 + 8 * nb + pi8(2 * tig + h);
+                        red_add_f64(acc_vv + row * ldacc + col, cvv[mb][nb][h]);
+                        red_add_f64(acc_vev + row * ldacc + col, cvev[mb][nb][h]);
+                        cvv[mb][nb][h] = 0.0;
+                        cvev[mb][nb][h] = 0.0;
+                    }
             }
+            kit = 0;
+            ++tile;
+        }
     }
 }
 

@@ -161,3 +161,41 @@ def test_compress_and_eigh(lib):
     assert relerr((u * w) @ u.T, a) < 1e-12
     with pytest.raises(lib.Agf2B200Error):
         lib.compress(-np.eye(5), np.eye(5))      # not SPD -> status, like the reference's LinAlgError
+
+
+def test_device_resident_async_and_sharded(lib):
+    """Device-resident C-ABI: two back-to-back asynchronous calls (occupied + virtual sector, as bench.py
+    issues them) and the part/nparts sharding used for multi-GPU (sum over parts == full build)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    o, v, n, p = 14, 50, 120, 70
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 12)
+    ixq2, qja2, ei2, ea2 = orc.synth_rhf(v, o, n, p, 13)      # virtual-sector call: roles swapped
+    T = lambda a, sh: torch.from_numpy(np.ascontiguousarray(a)).reshape(sh).to(dev)  # noqa: E731
+    d1 = (T(ixq, (o, p, n)), T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))
+    d2 = (T(ixq2, (v, p, n)), T(qja2, (n, v, o)), T(ei2, (v,)), T(ea2, (o,)))
+    out = torch.zeros((2, 2, p, p), dtype=torch.float64, device=dev)
+    for _ in range(3):      # repeated: scratch / staging reuse across in-flight calls
+        out.zero_()
+        lib.moments_rhf_dev(*d1, vv=out[0, 0], vev=out[0, 1], sync=False)
+        lib.moments_rhf_dev(*d2, vv=out[1, 0], vev=out[1, 1], sync=False)
+    torch.cuda.synchronize()
+    r1 = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o)
+    r2 = orc.np_build_part_loop_rhf(ixq2, qja2, ei2, ea2, p, v, o, n, 0, v)
+    h = out.cpu().numpy()
+    assert relerr(h[0, 0], r1[0]) < TOL and relerr(h[0, 1], r1[1]) < TOL
+    assert relerr(h[1, 0], r2[0]) < TOL and relerr(h[1, 1], r2[1]) < TOL
+    # sharding: 3 parts accumulate into the same output
+    acc = torch.zeros((2, p, p), dtype=torch.float64, device=dev)
+    for part in range(3):
+        lib.moments_rhf_dev(*d1, part=part, nparts=3, vv=acc[0], vev=acc[1], sync=True)
+    a = acc.cpu().numpy()
+    assert relerr(a[0], r1[0]) < TOL and relerr(a[1], r1[1]) < TOL
+    # padded leading dimensions (odd naux / nvir -> even pitch)
+    o, v, n, p = 5, 9, 21, 17
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 14)
+    ip = torch.zeros((o, p, n + 1), dtype=torch.float64, device=dev); ip[:, :, :n] = T(ixq, (o, p, n))
+    qp = torch.zeros((n, o, v + 1), dtype=torch.float64, device=dev); qp[:, :, :v] = T(qja, (n, o, v))
+    vv, vev = lib.moments_rhf_dev(ip, qp, T(ei, (o,)), T(ea, (v,)), naux=n)
+    r = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o)
+    assert relerr(vv.cpu().numpy(), r[0]) < TOL and relerr(vev.cpu().numpy(), r[1]) < TOL
