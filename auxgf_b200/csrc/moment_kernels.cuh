@@ -84,32 +84,40 @@ __device__ __forceinline__ void k1_mainloop(const uint8_t* __restrict__ gbase, u
     constexpr bool kDual = NB2 > 0;
     constexpr int kUnits = kDual ? 8 : 4;
 
+    // unit u -> (ks, e, block).  Register buffers: B fragments alternate with u (so the prefetch of unit
+    // u+1 never touches the registers unit u is reading); A fragments live for the two units of one
+    // (ks, block) and use buffer `block` (dual) or `ks & 1` (single block).
     auto load_unit = [&](const uint8_t* st, int u) {
         const int set = kDual ? (u & 1) : 0;
         const int e = kDual ? ((u >> 1) & 1) : (u & 1);
         const int ks = kDual ? (u >> 2) : (u >> 1);
+        const int abuf = kDual ? set : (ks & 1);
+        const int bbuf = u & 1;
         if (e == 0) {
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
-                fa[set][mb] = *reinterpret_cast<const double2*>(st + set * 16384 + a_off[ks] + mb * 1024);
+                fa[abuf][mb] = *reinterpret_cast<const double2*>(st + set * 16384 + a_off[ks] + mb * 1024);
         }
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb)
             if (nb < (set ? NB2 : NB1))
-                fb[set][nb] = *reinterpret_cast<const double*>(st + 32768 + set * 8192 + b_off[nb & 1][e] +
-                                                               (nb >> 1) * 2048 + ks * 1024);
+                fb[bbuf][nb] = *reinterpret_cast<const double*>(st + 32768 + set * 8192 + b_off[nb & 1][e] +
+                                                                (nb >> 1) * 2048 + ks * 1024);
     };
     auto compute_unit = [&](int u) {
         const int set = kDual ? (u & 1) : 0;
         const int e = kDual ? ((u >> 1) & 1) : (u & 1);
+        const int ks = kDual ? (u >> 2) : (u >> 1);
+        const int abuf = kDual ? set : (ks & 1);
+        const int bbuf = u & 1;
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb)
             if (nb < (set ? NB2 : NB1)) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
-                    const double a = e ? fa[set][mb].y : fa[set][mb].x;
-                    if (set) dmma884(acc2[mb][nb][0], acc2[mb][nb][1], a, fb[1][nb]);
-                    else dmma884(acc1[mb][nb][0], acc1[mb][nb][1], a, fb[0][nb]);
+                    const double a = e ? fa[abuf][mb].y : fa[abuf][mb].x;
+                    if (set) dmma884(acc2[mb][nb][0], acc2[mb][nb][1], a, fb[bbuf][nb]);
+                    else dmma884(acc1[mb][nb][0], acc1[mb][nb][1], a, fb[bbuf][nb]);
                 }
             }
     };

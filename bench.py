@@ -237,6 +237,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     checksum = float(out.sum().item())
+    out_host = out.cpu().numpy().copy()
 
     # per-kernel device time of one more (untimed) step, per-launch CUDA events inside the library
     lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, sync=True)
@@ -270,9 +271,12 @@ def main():
                 res = host_step()
             dt = (time.perf_counter() - t0) / max(1, min(args.steps, 2))
             chk2 = float(sum(a.sum() for r in res for a in r))
+            dev_vs_host = max(float(np.abs(res[k][m] - out_host[k, m]).max() / np.abs(out_host[k, m]).max())
+                              for k in range(2) for m in range(2))
             e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v),
                    "d2h_bytes_per_step": 4 * p * p * 8, "tflops": flops_build / dt * 1e-12,
                    "checksum_rel_diff_vs_device_path": abs(chk2 - checksum) / max(abs(checksum), 1e-300),
+                   "max_rel_diff_vs_device_path": dev_vs_host,
                    "api": "agf2_b200_build_part_loop_rhf (host pointers, pageable NumPy buffers)"}
         else:
             e2e = {"value": None, "unit": "s", "skipped": "host RAM %.0f GB < %.0f GB needed for the host copies" % (avail_gb, host_gb * 1.3 + 8)}
