@@ -492,7 +492,7 @@ int agf2_b200_moments_rhf_dev(const double* ixq, int64_t ld_ixq, const double* q
     if (int r = ensure_ctx()) return r;
     if (!ixq || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
     if (nocc <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    cudaStream_t st = (cudaStream_t)stream;   // used as given: 0 is the CUDA default stream
     std::vector<double> ei_h((size_t)nocc);
     CU_TRY(cudaMemcpyAsync(ei_h.data(), ei, nocc * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -517,7 +517,7 @@ int agf2_b200_moments_uhf_dev(const double* ixq_a, int64_t ld_ixq, const double*
     if (nocc_a <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
     const bool has_b = nocc_b > 0 && nvir_b > 0;
     if (has_b && (!qja_b || !ei_b || !ea_b)) return fail(AGF2_B200_EINVAL, "null pointer");
-    cudaStream_t st = stream ? (cudaStream_t)stream : g_ctx.stream;
+    cudaStream_t st = (cudaStream_t)stream;   // used as given: 0 is the CUDA default stream
     std::vector<double> eia((size_t)nocc_a), eib((size_t)std::max<int64_t>(nocc_b, 1));
     CU_TRY(cudaMemcpyAsync(eia.data(), ei_a, nocc_a * 8, cudaMemcpyDeviceToHost, st));
     if (has_b) CU_TRY(cudaMemcpyAsync(eib.data(), ei_b, nocc_b * 8, cudaMemcpyDeviceToHost, st));

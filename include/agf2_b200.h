@@ -100,8 +100,9 @@ int agf2_b200_build_part_loop_uhf(const double *ixq_a, const double *qja_a, cons
  * [part, nparts) -- items are dealt round-robin -- which is how the moment build is sharded over
  * the GPUs of one box (replaces the MPI split of auxgf/mpi/agf2/optragf2.py:370-374); the caller
  * sums the per-GPU vv/vev (one all-reduce).  Use part = 0, nparts = 1 for everything.
- * `stream` is a cudaStream_t (0 = the library's own stream); the call is asynchronous with
- * respect to the host unless `sync` is non-zero. */
+ * `stream` is a cudaStream_t, used as given (0 = the CUDA default stream).  All work is ordered on that
+ * stream; the library's scratch buffers are shared between calls, so concurrent calls must use the
+ * same stream.  The call is asynchronous with respect to the host unless `sync` is non-zero. */
 int agf2_b200_moments_rhf_dev(const double *ixq, int64_t ld_ixq, const double *qja, int64_t ld_qja,
                               const double *ei, const double *ea, int64_t nphys, int64_t nocc,
                               int64_t nvir, int64_t naux, int64_t istart, int64_t iend,
