@@ -129,6 +129,23 @@ int agf2_b200_compress(const double *vv, const double *vev, int64_t nphys, doubl
  * w: (n) ascending; v: (n, n) row-major with eigenvectors in COLUMNS (NumPy convention). */
 int agf2_b200_eigh(const double *a, int64_t n, double *w, double *v, int on_device);
 
+/* Device-resident DF tensor ("staged once to HBM") and the per-sector DF transform on the device.
+ *   agf2_b200_eri_create : eri is the Cholesky/DF tensor L, either tril-packed (naux, nphys(nphys+1)/2)
+ *       as OptRAGF2 keeps it (auxgf/agf2/optragf2.py:159-160, packed != 0) or full (naux, nphys, nphys);
+ *       host or device memory (on_device).  It is unpacked to (naux, nphys, nphys) in HBM.
+ *   agf2_b200_ao2mo_sector : replaces the two OptRAGF2.ao2mo calls of auxgf/agf2/optragf2.py:243-244
+ *       (pyscf _ao2mo.nr_e2, 's2' -> 's1'): from v_occ (nphys, nocc) and v_vir (nphys, nvir), row-major,
+ *       forms ixq (nocc, nphys, ld_ixq) and qja (naux, nocc, ld_qja) in handle-owned HBM scratch, in
+ *       exactly the layout agf2_b200_moments_*_dev consumes (valid until the next call on the handle). */
+typedef struct agf2_b200_eri agf2_b200_eri;
+int agf2_b200_eri_create(const double *eri, int64_t naux, int64_t nphys, int packed, int on_device,
+                         agf2_b200_eri **out);
+int agf2_b200_eri_destroy(agf2_b200_eri *h);
+int agf2_b200_eri_full_ptr(agf2_b200_eri *h, double **full);
+int agf2_b200_ao2mo_sector(agf2_b200_eri *h, const double *v_occ, int64_t nocc, const double *v_vir,
+                           int64_t nvir, int on_device, void *stream, double **ixq, int64_t *ld_ixq,
+                           double **qja, int64_t *ld_qja);
+
 /* Instrumentation: number of kernels launched by this library since the last reset, and the
  * device time (ms, CUDA events) of the last moments call's two kernels summed over launches. */
 int64_t agf2_b200_launch_count(int reset);
