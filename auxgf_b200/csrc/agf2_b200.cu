@@ -283,10 +283,12 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                 if (it.kind == 1 || it.kind == 3) {
                     const double eij = ei_same_host[it.i] + ei_same_host[it.j];
                     const long long c1 = col, c2 = (it.kind == 1 && ca != 0.0) ? col + w : col;
-                    for (int64_t a0 = 0; a0 < vpad; a0 += kTileN) {
-                        const int nb = (int)std::min<int64_t>(8, (vpad - a0) / 8);
-                        const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, v - a0));
-                        for (int xb = 0; xb < nxb; ++xb) {
+                    // tile order (pair, x-block, a-block): consecutive CTAs share the ixq rows of their
+                    // x-block and the (Q|ja) columns of their pair while those are still in L2
+                    for (int xb = 0; xb < nxb; ++xb) {
+                        for (int64_t a0 = 0; a0 < vpad; a0 += kTileN) {
+                            const int nb = (int)std::min<int64_t>(8, (vpad - a0) / 8);
+                            const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, v - a0));
                             K1Tile t;
                             memset(&t, 0, sizeof(t));
                             t.i1 = it.i; t.j1 = it.j; t.a1 = (int)a0; t.nb1 = nb;
@@ -340,8 +342,6 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                     tiles.push_back(t);
                 }
             }
-            std::stable_sort(tiles.begin(), tiles.end(),
-                             [](const K1Tile& a, const K1Tile& b) { return a.nb1 + a.nb2 > b.nb1 + b.nb2; });
 
             // ---- upload the tile list (double-buffered pinned staging) ----
             const int buf = (int)(chunk_idx & 1);

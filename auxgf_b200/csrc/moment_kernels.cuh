@@ -24,11 +24,14 @@ namespace agf2 {
 constexpr int kTileM = 128;        // rows (x) per CTA tile
 constexpr int kTileN = 64;         // max columns per integral block / moment tile
 constexpr int kKB = 16;            // K elements per pipeline stage (128 B rows -> SWIZZLE_128B)
-constexpr int kConsumerWarps = 8;  // each owns 16 rows x 64 cols
-// 8 warps = 2 per SM sub-partition -> up to 255 registers per thread.  (A ninth, dedicated TMA warp would
-// put 3 warps on one sub-partition and cap every thread at 168 registers.)  Lane 0 of warp 0 issues the
-// TMA loads kStages-2 iterations ahead, into the stage all warps released two iterations ago.
-constexpr int kThreads = kConsumerWarps * 32;
+constexpr int kConsumerWarps = 8;  // two consumer warpgroups; each warp owns 16 rows x 64 cols
+// + one producer warpgroup (only its first lane issues TMA).  12 warps cap the launch at 168 registers per
+// thread; setmaxnreg then moves registers from the producer warpgroup (40) to the consumers (232), which
+// hold 128 accumulator registers plus double-buffered fragments.
+constexpr int kThreads = (kConsumerWarps + 4) * 32;
+constexpr int kProducerRegs = 40, kConsumerRegs = 232;
+__device__ __forceinline__ void reg_dealloc_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs)); }
+__device__ __forceinline__ void reg_alloc_consumer() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs)); }
 
 // ---- K1 ---------------------------------------------------------------------------------------
 struct K1Tile {
@@ -57,10 +60,10 @@ __device__ __forceinline__ int pi8(int g) { return (g >> 1) | ((g & 1) << 2); }
 // One pipeline stage (16 Q) = 8 "units" (ks, e, set): the fragments of unit u+1 are loaded while the
 // DMMAs of unit u issue (they belong to the other block, so the registers are free), including across
 // the stage boundary, so shared-memory latency never sits between dependent instructions.
-template <int NB1, int NB2, typename Producer>
+template <int NB1, int NB2>
 __device__ __forceinline__ void k1_mainloop(const uint8_t* __restrict__ gbase, uint32_t bar_full, uint32_t bar_empty,
                                             int nk, int warp, int lane, double (&acc1)[2][8][2],
-                                            double (&acc2)[2][8][2], Producer& produce)
+                                            double (&acc2)[2][8][2])
 {
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
@@ -127,8 +130,6 @@ __device__ __forceinline__ void k1_mainloop(const uint8_t* __restrict__ gbase, u
     for (int it = 0; it < nk; ++it) {
         const int s = it % kK1Stages;
         const uint8_t* st = gbase + s * kK1StageBytes;
-        if (warp == 0 && lane == 0) produce(it + kK1Stages - 2);
-        __syncwarp();
 #pragma unroll
         for (int u = 0; u < kUnits; ++u) {
             if (u + 1 < kUnits) {
@@ -172,31 +173,35 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
     }
     __syncthreads();
 
-    // ===== TMA producer (executed by lane 0 of warp 0): loads of pipeline iteration j =====
-    const int ng1 = (t.nb1 + 1) >> 1, ng2 = (t.nb2 + 1) >> 1;   // 16-column TMA boxes
-    const uint32_t stage_tx = (uint32_t)((t.nb1 ? kTileM * kKB * 8 : 0) + (t.nb2 ? kTileM * kKB * 8 : 0) +
-                                         (ng1 + ng2) * 16 * kKB * 8);
-    auto produce = [&](int j) {
-        if (j >= nk) return;
-        const int s = j % kK1Stages;
-        if (j >= kK1Stages) mbar_wait(bar_empty + 8 * s, ((j / kK1Stages) - 1) & 1);
-        const uint32_t st = base + s * kK1StageBytes;
-        const uint32_t fb = bar_full + 8 * s;
-        const CUtensorMap* mB1 = t.bsel1 ? &mapB1 : &mapB0;
-        const CUtensorMap* mB2 = t.bsel2 ? &mapB1 : &mapB0;
-        mbar_expect_tx(fb, stage_tx);
-        const int q0 = j * kKB;
-        if (t.nb1) tma_load_3d(st, &mapA, q0, t.xb * kTileM, t.i1, fb);
-        if (t.nb2) tma_load_3d(st + 16384, &mapA, q0, t.xb * kTileM, t.i2, fb);
-        for (int g = 0; g < ng1; ++g) tma_load_3d(st + 32768 + g * 2048, mB1, t.a1 + 16 * g, t.j1, q0, fb);
-        for (int g = 0; g < ng2; ++g) tma_load_3d(st + 40960 + g * 2048, mB2, t.a2 + 16 * g, t.j2, q0, fb);
-    };
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(t.bsel1 ? &mapB1 : &mapB0);
-        for (int j = 0; j < kK1Stages - 2; ++j) produce(j);
+    // ===== producer warpgroup: one lane streams the operand tiles through the mbarrier ring =====
+    if (warp >= kConsumerWarps) {
+        reg_dealloc_producer();
+        if (warp == kConsumerWarps && lane == 0) {
+            tma_prefetch_desc(&mapA);
+            tma_prefetch_desc(t.bsel1 ? &mapB1 : &mapB0);
+            const int ng1 = (t.nb1 + 1) >> 1, ng2 = (t.nb2 + 1) >> 1;   // 16-column TMA boxes
+            const uint32_t stage_tx = (uint32_t)((t.nb1 ? kTileM * kKB * 8 : 0) + (t.nb2 ? kTileM * kKB * 8 : 0) +
+                                                 (ng1 + ng2) * 16 * kKB * 8);
+            const CUtensorMap* mB1 = t.bsel1 ? &mapB1 : &mapB0;
+            const CUtensorMap* mB2 = t.bsel2 ? &mapB1 : &mapB0;
+            const int nb1 = t.nb1, nb2 = t.nb2, x0 = t.xb * kTileM, i1 = t.i1, i2 = t.i2, j1 = t.j1, j2 = t.j2,
+                      a1 = t.a1, a2 = t.a2;
+            for (int j = 0; j < nk; ++j) {
+                const int s = j % kK1Stages;
+                if (j >= kK1Stages) mbar_wait(bar_empty + 8 * s, ((j / kK1Stages) - 1) & 1);
+                const uint32_t st = base + s * kK1StageBytes;
+                const uint32_t fb = bar_full + 8 * s;
+                mbar_expect_tx(fb, stage_tx);
+                const int q0 = j * kKB;
+                if (nb1) tma_load_3d(st, &mapA, q0, x0, i1, fb);
+                if (nb2) tma_load_3d(st + 16384, &mapA, q0, x0, i2, fb);
+                for (int g = 0; g < ng1; ++g) tma_load_3d(st + 32768 + g * 2048, mB1, a1 + 16 * g, j1, q0, fb);
+                for (int g = 0; g < ng2; ++g) tma_load_3d(st + 40960 + g * 2048, mB2, a2 + 16 * g, j2, q0, fb);
+            }
+        }
+        return;
     }
-    __syncwarp();
+    reg_alloc_consumer();
 
     // ===== consumers: 8 warps x (16 rows x 64 cols x 2 blocks) =====
     const int gid = lane >> 2, tig = lane & 3;
@@ -211,7 +216,7 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
         }
     const int nb1 = t.nb1, nb2 = t.nb2;
     switch (nb1 * 16 + nb2) {
-#define AGF2_K1_CASE(A, B) case (A) * 16 + (B): k1_mainloop<A, B>(gbase, bar_full, bar_empty, nk, warp, lane, acc1, acc2, produce); break;
+#define AGF2_K1_CASE(A, B) case (A) * 16 + (B): k1_mainloop<A, B>(gbase, bar_full, bar_empty, nk, warp, lane, acc1, acc2); break;
         AGF2_K1_CASE(8, 8) AGF2_K1_CASE(7, 7) AGF2_K1_CASE(6, 6) AGF2_K1_CASE(5, 5)
         AGF2_K1_CASE(4, 4) AGF2_K1_CASE(3, 3) AGF2_K1_CASE(2, 2) AGF2_K1_CASE(1, 1)
         AGF2_K1_CASE(8, 0) AGF2_K1_CASE(7, 0) AGF2_K1_CASE(6, 0) AGF2_K1_CASE(5, 0)
@@ -308,29 +313,32 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
     __syncthreads();
     if (nk <= 0) return;
 
-    // ===== TMA producer (lane 0 of warp 0) =====
-    auto produce = [&](int j) {
-        if (j >= nk) return;
-        constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8;
-        const int s = j % kK2Stages;
-        if (j >= kK2Stages) mbar_wait(bar_empty + 8 * s, ((j / kK2Stages) - 1) & 1);
-        const uint32_t st = base + s * kK2StageBytes;
-        const uint32_t fb = bar_full + 8 * s;
-        mbar_expect_tx(fb, bytes);
-        const long long L = L0 + j;
-        const K2Tile t = tiles[L / nk_total];
-        const int k0 = (int)(L % nk_total) * kKB;
-        tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
-        tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
-        tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
-        bulk_load_1d(st + 24576, E + k0, kKB * 8, fb);
-    };
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&mapWA);
-        tma_prefetch_desc(&mapWB);
-        for (int j = 0; j < kK2Stages - 2; ++j) produce(j);
+    // ===== producer warpgroup =====
+    if (warp >= kConsumerWarps) {
+        reg_dealloc_producer();
+        if (warp == kConsumerWarps && lane == 0) {
+            tma_prefetch_desc(&mapWA);
+            tma_prefetch_desc(&mapWB);
+            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8;
+            int tile = (int)(L0 / nk_total), kit = (int)(L0 % nk_total);
+            K2Tile t = tiles[tile];
+            for (int j = 0; j < nk; ++j) {
+                const int s = j % kK2Stages;
+                if (j >= kK2Stages) mbar_wait(bar_empty + 8 * s, ((j / kK2Stages) - 1) & 1);
+                const uint32_t st = base + s * kK2StageBytes;
+                const uint32_t fb = bar_full + 8 * s;
+                mbar_expect_tx(fb, bytes);
+                const int k0 = kit * kKB;
+                tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
+                tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
+                tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
+                bulk_load_1d(st + 24576, E + k0, kKB * 8, fb);
+                if (++kit == nk_total && j + 1 < nk) { kit = 0; t = tiles[++tile]; }
+            }
+        }
+        return;
     }
-    __syncwarp();
+    reg_alloc_consumer();
 
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
@@ -389,8 +397,6 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
     for (int it = 0; it < nk; ++it) {
         const int s = it % kK2Stages;
         const uint8_t* st = gbase + s * kK2StageBytes;
-        if (warp == 0 && lane == 0) produce(it + kK2Stages - 2);
-        __syncwarp();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (u < 3) {

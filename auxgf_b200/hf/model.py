@@ -44,7 +44,7 @@ class ModelRHF:
     """Closed-shell model molecule: ``ModelRHF(nao, nocc, naux, seed).run()``."""
     with_df = True
 
-    def __init__(self, nao=12, nocc=4, naux=30, seed=0, strength=0.9, e_nuc=1.0):
+    def __init__(self, nao=12, nocc=4, naux=30, seed=0, strength=0.5, e_nuc=1.0):
         self.nao, self.nocc_hf, self.naux = nao, nocc, naux
         self.seed, self.strength = seed, strength
         self.mol = Molecule(e_nuc=e_nuc)
@@ -121,7 +121,7 @@ class ModelUHF:
     """Open-shell model molecule (nalph != nbeta allowed)."""
     with_df = True
 
-    def __init__(self, nao=12, nalph=4, nbeta=3, naux=30, seed=0, strength=0.9, e_nuc=1.0):
+    def __init__(self, nao=12, nalph=4, nbeta=3, naux=30, seed=0, strength=0.5, e_nuc=1.0):
         self.nao, self.nalph, self.nbeta, self.naux = nao, nalph, nbeta, naux
         self.seed, self.strength = seed, strength
         self.mol = Molecule(e_nuc=e_nuc)

@@ -283,3 +283,107 @@ def eigh_dev(a):
     torch.cuda.current_stream(a.device).synchronize()
     check(_libagf2.agf2_b200_eigh(a.data_ptr(), n, w.data_ptr(), v.data_ptr(), 1))
     return w, v
+
+
+# ---- device-resident DF tensor + fused sector build ---------------------------------------------
+_libagf2.agf2_b200_ao2mo_last_error.restype = ctypes.c_char_p
+_libagf2.agf2_b200_eri_create.argtypes = [_vp, _i64, _i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]
+_libagf2.agf2_b200_eri_destroy.argtypes = [_vp]
+_libagf2.agf2_b200_eri_full_ptr.argtypes = [_vp, ctypes.POINTER(_vp)]
+_libagf2.agf2_b200_ao2mo_sector.argtypes = [_vp, _vp, _i64, _vp, _i64, ctypes.c_int, _vp, ctypes.POINTER(_vp),
+                                            ctypes.POINTER(_i64), ctypes.POINTER(_vp), ctypes.POINTER(_i64)]
+SYMBOLS += ["agf2_b200_eri_create", "agf2_b200_eri_destroy", "agf2_b200_eri_full_ptr", "agf2_b200_ao2mo_sector"]
+
+
+def _check2(status):
+    if status != 0:
+        msg = _libagf2.agf2_b200_ao2mo_last_error().decode() or _libagf2.agf2_b200_last_error().decode()
+        raise Agf2B200Error("libagf2_b200 error %d: %s" % (status, msg))
+
+
+class DeviceERI:
+    """The DF tensor L (naux, nphys, nphys) staged once to HBM, plus the per-sector pipeline
+    ao2mo -> moment build on the device (replaces optragf2.py:243-268 with no host round trip of
+    ixq/qja).  ``eri`` is a host NumPy array: tril-packed (naux, nphys(nphys+1)/2) or (naux, nphys, nphys)."""
+
+    def __init__(self, eri, nphys=None, packed=None):
+        eri = np.ascontiguousarray(eri, dtype=_f64)
+        if packed is None:
+            packed = eri.ndim == 2
+        if packed:
+            naux = eri.shape[0]
+            if nphys is None:
+                nphys = int((np.sqrt(8 * eri.shape[1] + 1) - 1) / 2)
+            assert eri.shape[1] == nphys * (nphys + 1) // 2
+        else:
+            eri = eri.reshape(eri.shape[0], -1)
+            naux = eri.shape[0]
+            nphys = int(round(np.sqrt(eri.shape[1]))) if nphys is None else nphys
+            assert eri.shape[1] == nphys * nphys
+        self.naux, self.nphys = naux, nphys
+        h = _vp()
+        _check2(_libagf2.agf2_b200_eri_create(eri.ctypes.data, naux, nphys, 1 if packed else 0, 0, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _libagf2.agf2_b200_eri_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+
+    def sector(self, v_occ, v_vir):
+        """(ix|Q), (Q|ja) for one sector -> raw device pointers (ixq, ld_ixq, qja, ld_qja)."""
+        v_occ = _c(v_occ, 2); v_vir = _c(v_vir, 2)
+        assert v_occ.shape[0] == self.nphys and v_vir.shape[0] == self.nphys
+        ixq, qja, ldi, ldq = _vp(), _vp(), _i64(), _i64()
+        _check2(_libagf2.agf2_b200_ao2mo_sector(self._h, v_occ.ctypes.data, v_occ.shape[1], v_vir.ctypes.data,
+                                                v_vir.shape[1], 0, self._stream(), ctypes.byref(ixq),
+                                                ctypes.byref(ldi), ctypes.byref(qja), ctypes.byref(ldq)))
+        return ixq.value, ldi.value, qja.value, ldq.value
+
+    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+        """vv, vev (CUDA tensors) of one sector, everything on the device."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nphys, nocc, nvir = self.nphys, gf_occ.naux, gf_vir.naux
+        ixq, ldi, qja, ldq = self.sector(gf_occ.v, gf_vir.v)
+        ei = torch.from_numpy(_c(gf_occ.e, 1)).to(dev)
+        ea = torch.from_numpy(_c(gf_vir.e, 1)).to(dev)
+        out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
+        check(_libagf2.agf2_b200_moments_rhf_dev(ixq, ldi, qja, ldq, ei.data_ptr(), ea.data_ptr(), nphys, nocc,
+                                                 nvir, self.naux, 0, nocc, os_factor, ss_factor, part, nparts,
+                                                 out[0].data_ptr(), out[1].data_ptr(), self._stream(), 1))
+        return out
+
+    @staticmethod
+    def compress(mom):
+        """cuSOLVER pole compression of a packed [vv|vev] CUDA tensor -> host (e, c)."""
+        e, c = compress_dev(mom[0], mom[1])
+        return e.cpu().numpy(), c.cpu().numpy()
+
+    @staticmethod
+    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+        """One spin channel of OptUAGF2.build_part: eri_a/gf_*[0] same spin, eri_b/gf_*[1] opposite spin."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nphys = eri_a.nphys
+        ixq, ldi, qja, ldq = eri_a.sector(gf_occ[0].v, gf_vir[0].v)
+        _, _, qjb, ldqb = eri_b.sector(gf_occ[1].v, gf_vir[1].v)
+        T = lambda a: torch.from_numpy(_c(a, 1)).to(dev)  # noqa: E731
+        eia, eib, eaa, eab = T(gf_occ[0].e), T(gf_occ[1].e), T(gf_vir[0].e), T(gf_vir[1].e)
+        out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
+        check(_libagf2.agf2_b200_moments_uhf_dev(ixq, ldi, qja, ldq, qjb, ldqb, eia.data_ptr(), eib.data_ptr(),
+                                                 eaa.data_ptr(), eab.data_ptr(), nphys, gf_occ[0].naux,
+                                                 gf_occ[1].naux, gf_vir[0].naux, gf_vir[1].naux, eri_a.naux, 0,
+                                                 gf_occ[0].naux, os_factor, ss_factor, part, nparts,
+                                                 out[0].data_ptr(), out[1].data_ptr(), eri_a._stream(), 1))
+        return out

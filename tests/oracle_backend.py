@@ -1,0 +1,72 @@
+"""TEST-ONLY backend: routes the drivers' compute calls to the CPU oracle (oracle/agf2_oracle.py) so that
+the host-side driver logic (Aux, Fock loop, energies, multi-rank sharding) can be exercised without a
+GPU, and so that GPU runs can be compared driver-to-driver.  Never imported by the package."""
+import numpy as np
+
+from oracle import agf2_oracle as orc
+
+
+class _HostERI:
+    def __init__(self, eri, nphys, packed):
+        eri = np.asarray(eri, dtype=np.float64)
+        self.nphys = nphys
+        self.full = orc.np_unpack_tril(eri, nphys) if packed else eri.reshape(-1, nphys, nphys)
+        self.naux = self.full.shape[0]
+
+    def _blocks(self, v_occ, v_vir):
+        ixq = np.einsum("Qxp,pi->ixQ", self.full, v_occ, optimize=True)
+        qja = np.einsum("jxQ,xa->Qja", ixq, v_vir, optimize=True)
+        return ixq, qja
+
+    def sector(self, v_occ, v_vir):
+        return self._blocks(v_occ, v_vir)
+
+    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+        o, v, p = gf_occ.naux, gf_vir.naux, self.nphys
+        ixq, qja = self._blocks(gf_occ.v, gf_vir.v)
+        # the oracle shards by contiguous pole slices (auxgf/mpi/agf2/optragf2.py:370-374)
+        lo, hi = (o * part) // nparts, (o * (part + 1)) // nparts
+        vv, vev = orc.np_build_part_loop_rhf(ixq.reshape(o * p, -1), qja.reshape(self.naux, -1), gf_occ.e, gf_vir.e,
+                                             p, o, v, self.naux, lo, hi, os_factor, ss_factor)
+        return _Packed(np.stack([vv, vev]))
+
+    @staticmethod
+    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+        p = eri_a.nphys
+        oa, ob, va, vb = gf_occ[0].naux, gf_occ[1].naux, gf_vir[0].naux, gf_vir[1].naux
+        ixq_a, qja_a = eri_a._blocks(gf_occ[0].v, gf_vir[0].v)
+        _, qja_b = eri_b._blocks(gf_occ[1].v, gf_vir[1].v)
+        lo, hi = (oa * part) // nparts, (oa * (part + 1)) // nparts
+        vv, vev = orc.np_build_part_loop_uhf(ixq_a.reshape(oa * p, -1), qja_a.reshape(eri_a.naux, -1),
+                                             qja_b.reshape(eri_a.naux, -1), gf_occ[0].e, gf_occ[1].e, gf_vir[0].e,
+                                             gf_vir[1].e, p, oa, ob, va, vb, eri_a.naux, lo, hi, os_factor, ss_factor)
+        return _Packed(np.stack([vv, vev]))
+
+    @staticmethod
+    def compress(mom):
+        return orc.np_compress(mom.a[0], mom.a[1])
+
+
+class _Packed:
+    """Host stand-in for the packed [vv|vev] CUDA tensor; all-reduced through torch.distributed (gloo)."""
+    def __init__(self, a):
+        self.a = a
+
+
+class OracleBackend:
+    name = "oracle"
+
+    def build_part_loop_rhf(self, ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None, os_factor=1.0, ss_factor=1.0):
+        o, v, p = gf_occ.naux, gf_vir.naux, gf_occ.nphys
+        ixq = np.asarray(ixq).reshape(o * p, -1)
+        return orc.np_build_part_loop_rhf(ixq, np.asarray(qja).reshape(ixq.shape[1], -1), gf_occ.e, gf_vir.e, p, o, v,
+                                          ixq.shape[1], istart, iend, os_factor, ss_factor, vv, vev)
+
+    def compress(self, vv, vev):
+        return orc.np_compress(vv, vev)
+
+    def eigh(self, a):
+        return np.linalg.eigh(a)
+
+    def stage_eri(self, eri, nphys, sym_in="s2"):
+        return _HostERI(eri, nphys, packed=(sym_in == "s2"))
