@@ -57,10 +57,13 @@ struct Ctx {
     bool simple = false;
     bool profile = true;
     // scratch
-    double* W[2] = {nullptr, nullptr};
+    double* W[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [ring buffer][W0 | W1]
     size_t w_elems = 0;
-    double* E = nullptr;
-    size_t e_elems = 0;
+    double* E[2] = {nullptr, nullptr};
+    size_t e_elems[2] = {0, 0};
+    bool overlap = true;               // k2_moment of chunk c on a second stream, under k1_form of chunk c+1
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr}, ev_start = nullptr;
     double* acc = nullptr;   // 4 accumulators: S_vv, S_vev, A_vv, A_vev
     size_t acc_elems = 0;
     K1Tile* d_t1[2] = {nullptr, nullptr};
@@ -104,7 +107,18 @@ int ensure_ctx() {
     c.encode = reinterpret_cast<EncodeTiledFn>(fn);
     CU_TRY(cudaFuncSetAttribute(k1_form, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
     CU_TRY(cudaFuncSetAttribute(k2_moment, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
-    for (int b = 0; b < 2; ++b) CU_TRY(cudaEventCreateWithFlags(&c.t1_free[b], cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CU_TRY(cudaEventCreateWithFlags(&c.t1_free[b], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c.ev_k1[b], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c.ev_k2[b], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
+    {
+        int lo = 0, hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_TRY(cudaStreamCreateWithPriority(&c.stream2, cudaStreamNonBlocking, hi));   // k2 drains first
+    }
+    if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
     if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
     c.init = true;
@@ -196,20 +210,30 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     cap_cols = rup(cap_cols, 16);
     const size_t w_need = (size_t)p_pad * cap_cols;
     if (w_need > c.w_elems) {
-        for (int b = 0; b < 2; ++b) { if (c.W[b]) cudaFree(c.W[b]); c.W[b] = nullptr; }
+        CU_TRY(cudaDeviceSynchronize());
+        for (int r = 0; r < 2; ++r)
+            for (int b = 0; b < 2; ++b) { if (c.W[r][b]) cudaFree(c.W[r][b]); c.W[r][b] = nullptr; }
         c.w_elems = 0;
-        for (int b = 0; b < 2; ++b) {
-            CU_TRY(cudaMalloc(&c.W[b], w_need * 8));
-            CU_TRY(cudaMemset(c.W[b], 0, w_need * 8));
-        }
+        for (int r = 0; r < 2; ++r)
+            for (int b = 0; b < 2; ++b) {
+                CU_TRY(cudaMalloc(&c.W[r][b], w_need * 8));
+                CU_TRY(cudaMemset(c.W[r][b], 0, w_need * 8));
+            }
         c.w_elems = w_need;
     }
     const int64_t ldw = cap_cols;
-    { int r = grow(c.E, c.e_elems, (size_t)cap_cols + 64, true); if (r) return r; }
+    for (int r = 0; r < 2; ++r) { int rc = grow(c.E[r], c.e_elems[r], (size_t)cap_cols + 64, true); if (rc) return rc; }
     { int r = grow(c.acc, c.acc_elems, (size_t)4 * p_pad * p_pad, false); if (r) return r; }
     const size_t acc_n = (size_t)p_pad * p_pad;
     double* S_vv = c.acc; double* S_vev = c.acc + acc_n; double* A_vv = c.acc + 2 * acc_n; double* A_vev = c.acc + 3 * acc_n;
     CU_TRY(cudaMemsetAsync(c.acc, 0, 4 * acc_n * 8, st));
+    const bool overlap = c.overlap && !c.simple;
+    cudaStream_t st2 = overlap ? c.stream2 : st;
+    if (overlap) {
+        CU_TRY(cudaEventRecord(c.ev_start, st));
+        CU_TRY(cudaStreamWaitEvent(st2, c.ev_start, 0));
+    }
+    bool k2_pending[2] = {false, false};
 
     // ---- TMA descriptors of the inputs ----------------------------------------------------------
     CUtensorMap mapA, mapB0, mapB1;
@@ -367,21 +391,29 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             CU_TRY(cudaMemcpyAsync(c.d_t1[buf], c.h_t1[buf], tiles.size() * sizeof(K1Tile), cudaMemcpyHostToDevice, st));
 
             // ---- K1: form the integral blocks of this chunk ----
+            double* const Wa = c.W[buf][0];
+            double* const Wb = c.W[buf][1];
+            double* const Ebuf = c.E[buf];
+            if (overlap && k2_pending[buf]) CU_TRY(cudaStreamWaitEvent(st, c.ev_k2[buf], 0));
             record(st, 0, true);
             if (!c.simple) {
                 k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, st>>>(
-                    mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev, c.W[0], c.W[1],
-                    c.E, ldw, nk1);
+                    mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev, Wa, Wb,
+                    Ebuf, ldw, nk1);
             } else {
                 k1_form_simple<<<(unsigned)tiles.size(), 256, 0, st>>>(
                     ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,
                     other ? other->qja : same.qja, other ? other->ld : same.ld, other ? (int)other->nocc : (int)o,
                     other ? (int)other->nvir : (int)v, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
-                    c.W[0], c.W[1], c.E, ldw);
+                    Wa, Wb, Ebuf, ldw);
             }
             record(st, 0, false);
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaEventRecord(c.t1_free[buf], st));
+            if (overlap) {
+                CU_TRY(cudaEventRecord(c.ev_k1[buf], st));
+                CU_TRY(cudaStreamWaitEvent(st2, c.ev_k1[buf], 0));
+            }
             c.launches++;
 
             // ---- K2: accumulate the moments of this chunk ----
@@ -391,22 +423,26 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             // stream-K grid: one CTA per SM, unless the chunk is too small to give each >= 8 iterations
             const long long total_it = (long long)t2.size() * nk2;
             const int grid2 = (int)std::max<long long>(1, std::min<long long>(c.num_sms, total_it / 8));
-            record(st, 1, true);
+            record(st2, 1, true);
             if (!c.simple) {
                 CUtensorMap mapWA, mapWB;
                 cuuint64_t d[2] = {(cuuint64_t)col, (cuuint64_t)p_pad};
                 cuuint64_t s[1] = {(cuuint64_t)ldw * 8};
                 cuuint32_t b[2] = {kKB, 64};
-                if (int r = make_map(&mapWA, c.W[0], 2, d, s, b)) return r;
-                if (int r = make_map(&mapWB, sym ? c.W[0] : c.W[1], 2, d, s, b)) return r;
-                k2_moment<<<grid2, kThreads, kK2SmemBytes, st>>>(mapWA, mapWB, c.E, d_t2, sym ? S_vv : A_vv,
+                if (int r = make_map(&mapWA, Wa, 2, d, s, b)) return r;
+                if (int r = make_map(&mapWB, sym ? Wa : Wb, 2, d, s, b)) return r;
+                k2_moment<<<grid2, kThreads, kK2SmemBytes, st2>>>(mapWA, mapWB, Ebuf, d_t2, sym ? S_vv : A_vv,
                                                                 sym ? S_vev : A_vev, p_pad, nk2, (int)t2.size());
             } else {
-                k2_moment_simple<<<(unsigned)t2.size(), 256, 0, st>>>(c.W[0], sym ? c.W[0] : c.W[1], ldw, c.E, (int)col,
+                k2_moment_simple<<<(unsigned)t2.size(), 256, 0, st2>>>(Wa, sym ? Wa : Wb, ldw, Ebuf, (int)col,
                                                                       d_t2, sym ? S_vv : A_vv, sym ? S_vev : A_vev, p_pad);
             }
-            record(st, 1, false);
+            record(st2, 1, false);
             CU_TRY(cudaGetLastError());
+            if (overlap) {
+                CU_TRY(cudaEventRecord(c.ev_k2[buf], st2));
+                k2_pending[buf] = true;
+            }
             c.launches++;
             ++chunk_idx;
         }
@@ -416,6 +452,9 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     if (int r = run_chunks(sym_items, true)) return r;
     if (int r = run_chunks(asym_items, false)) return r;
 
+    if (overlap)
+        for (int b = 0; b < 2; ++b)
+            if (k2_pending[b]) CU_TRY(cudaStreamWaitEvent(st, c.ev_k2[b], 0));
     dim3 g3((unsigned)((nphys + 127) / 128), (unsigned)nphys);
     k3_finalize<<<g3, 128, 0, st>>>(S_vv, S_vev, asym_items.empty() ? nullptr : A_vv, asym_items.empty() ? nullptr : A_vev,
                                     p_pad, (int)nphys, vv, vev);
