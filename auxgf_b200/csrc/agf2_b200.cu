@@ -61,7 +61,7 @@ struct Ctx {
     size_t w_elems = 0;
     double* E[2] = {nullptr, nullptr};
     size_t e_elems[2] = {0, 0};
-    bool overlap = true;               // k2_moment of chunk c on a second stream, under k1_form of chunk c+1
+    bool overlap = true;               // odd chunks run on a second stream: one chain's tail is filled by the other
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr}, ev_start = nullptr;
     double* acc = nullptr;   // 4 accumulators: S_vv, S_vev, A_vv, A_vev
@@ -113,11 +113,7 @@ int ensure_ctx() {
         CU_TRY(cudaEventCreateWithFlags(&c.ev_k2[b], cudaEventDisableTiming));
     }
     CU_TRY(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
-    {
-        int lo = 0, hi = 0;
-        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU_TRY(cudaStreamCreateWithPriority(&c.stream2, cudaStreamNonBlocking, hi));   // k2 drains first
-    }
+    CU_TRY(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
     if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
     if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
@@ -228,12 +224,14 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     double* S_vv = c.acc; double* S_vev = c.acc + acc_n; double* A_vv = c.acc + 2 * acc_n; double* A_vev = c.acc + 3 * acc_n;
     CU_TRY(cudaMemsetAsync(c.acc, 0, 4 * acc_n * 8, st));
     const bool overlap = c.overlap && !c.simple;
-    cudaStream_t st2 = overlap ? c.stream2 : st;
+    // Two independent chains: chunk c runs k1_form -> k2_moment on stream (c & 1) with ring buffer (c & 1),
+    // so buffer reuse is ordered by the stream itself and the CTAs of one chain fill the SMs that the tail
+    // of the other chain's kernel leaves idle.
     if (overlap) {
         CU_TRY(cudaEventRecord(c.ev_start, st));
-        CU_TRY(cudaStreamWaitEvent(st2, c.ev_start, 0));
+        CU_TRY(cudaStreamWaitEvent(c.stream2, c.ev_start, 0));
     }
-    bool k2_pending[2] = {false, false};
+    bool used2 = false;
 
     // ---- TMA descriptors of the inputs ----------------------------------------------------------
     CUtensorMap mapA, mapB0, mapB1;
@@ -369,6 +367,8 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
 
             // ---- upload the tile list (double-buffered pinned staging) ----
             const int buf = (int)(chunk_idx & 1);
+            cudaStream_t sc = (overlap && buf) ? c.stream2 : st;
+            if (sc != st) used2 = true;
             if (tiles.size() > c.t1_cap) {
                 CU_TRY(cudaStreamSynchronize(st));
                 for (int b = 0; b < 2; ++b) {
@@ -388,32 +388,27 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                 CU_TRY(cudaEventSynchronize(c.t1_free[buf]));
             }
             memcpy(c.h_t1[buf], tiles.data(), tiles.size() * sizeof(K1Tile));
-            CU_TRY(cudaMemcpyAsync(c.d_t1[buf], c.h_t1[buf], tiles.size() * sizeof(K1Tile), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemcpyAsync(c.d_t1[buf], c.h_t1[buf], tiles.size() * sizeof(K1Tile), cudaMemcpyHostToDevice, sc));
 
             // ---- K1: form the integral blocks of this chunk ----
             double* const Wa = c.W[buf][0];
             double* const Wb = c.W[buf][1];
             double* const Ebuf = c.E[buf];
-            if (overlap && k2_pending[buf]) CU_TRY(cudaStreamWaitEvent(st, c.ev_k2[buf], 0));
-            record(st, 0, true);
+            record(sc, 0, true);
             if (!c.simple) {
-                k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, st>>>(
+                k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, sc>>>(
                     mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev, Wa, Wb,
                     Ebuf, ldw, nk1);
             } else {
-                k1_form_simple<<<(unsigned)tiles.size(), 256, 0, st>>>(
+                k1_form_simple<<<(unsigned)tiles.size(), 256, 0, sc>>>(
                     ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,
                     other ? other->qja : same.qja, other ? other->ld : same.ld, other ? (int)other->nocc : (int)o,
                     other ? (int)other->nvir : (int)v, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
                     Wa, Wb, Ebuf, ldw);
             }
-            record(st, 0, false);
+            record(sc, 0, false);
             CU_TRY(cudaGetLastError());
-            CU_TRY(cudaEventRecord(c.t1_free[buf], st));
-            if (overlap) {
-                CU_TRY(cudaEventRecord(c.ev_k1[buf], st));
-                CU_TRY(cudaStreamWaitEvent(st2, c.ev_k1[buf], 0));
-            }
+            CU_TRY(cudaEventRecord(c.t1_free[buf], sc));
             c.launches++;
 
             // ---- K2: accumulate the moments of this chunk ----
@@ -423,7 +418,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             // stream-K grid: one CTA per SM, unless the chunk is too small to give each >= 8 iterations
             const long long total_it = (long long)t2.size() * nk2;
             const int grid2 = (int)std::max<long long>(1, std::min<long long>(c.num_sms, total_it / 8));
-            record(st2, 1, true);
+            record(sc, 1, true);
             if (!c.simple) {
                 CUtensorMap mapWA, mapWB;
                 cuuint64_t d[2] = {(cuuint64_t)col, (cuuint64_t)p_pad};
@@ -431,18 +426,14 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                 cuuint32_t b[2] = {kKB, 64};
                 if (int r = make_map(&mapWA, Wa, 2, d, s, b)) return r;
                 if (int r = make_map(&mapWB, sym ? Wa : Wb, 2, d, s, b)) return r;
-                k2_moment<<<grid2, kThreads, kK2SmemBytes, st2>>>(mapWA, mapWB, Ebuf, d_t2, sym ? S_vv : A_vv,
+                k2_moment<<<grid2, kThreads, kK2SmemBytes, sc>>>(mapWA, mapWB, Ebuf, d_t2, sym ? S_vv : A_vv,
                                                                 sym ? S_vev : A_vev, p_pad, nk2, (int)t2.size());
             } else {
-                k2_moment_simple<<<(unsigned)t2.size(), 256, 0, st2>>>(Wa, sym ? Wa : Wb, ldw, Ebuf, (int)col,
+                k2_moment_simple<<<(unsigned)t2.size(), 256, 0, sc>>>(Wa, sym ? Wa : Wb, ldw, Ebuf, (int)col,
                                                                       d_t2, sym ? S_vv : A_vv, sym ? S_vev : A_vev, p_pad);
             }
-            record(st2, 1, false);
+            record(sc, 1, false);
             CU_TRY(cudaGetLastError());
-            if (overlap) {
-                CU_TRY(cudaEventRecord(c.ev_k2[buf], st2));
-                k2_pending[buf] = true;
-            }
             c.launches++;
             ++chunk_idx;
         }
@@ -452,9 +443,10 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     if (int r = run_chunks(sym_items, true)) return r;
     if (int r = run_chunks(asym_items, false)) return r;
 
-    if (overlap)
-        for (int b = 0; b < 2; ++b)
-            if (k2_pending[b]) CU_TRY(cudaStreamWaitEvent(st, c.ev_k2[b], 0));
+    if (used2) {
+        CU_TRY(cudaEventRecord(c.ev_k2[0], c.stream2));
+        CU_TRY(cudaStreamWaitEvent(st, c.ev_k2[0], 0));
+    }
     dim3 g3((unsigned)((nphys + 127) / 128), (unsigned)nphys);
     k3_finalize<<<g3, 128, 0, st>>>(S_vv, S_vev, asym_items.empty() ? nullptr : A_vv, asym_items.empty() ? nullptr : A_vev,
                                     p_pad, (int)nphys, vv, vev);
