@@ -503,6 +503,11 @@ int agf2_b200_set_simple_kernels(int on) {
     return 0;
 }
 
+int agf2_b200_set_overlap(int on) {
+    g_ctx.overlap = on != 0;
+    return 0;
+}
+
 int64_t agf2_b200_launch_count(int reset) {
     const int64_t n = g_ctx.launches;
     if (reset) g_ctx.launches = 0;

@@ -31,7 +31,7 @@ SYMBOLS = [
     "agf2_b200_set_device", "agf2_b200_set_workspace_bytes", "agf2_b200_build_part_loop_rhf",
     "agf2_b200_build_part_loop_uhf", "agf2_b200_moments_rhf_dev", "agf2_b200_moments_uhf_dev",
     "agf2_b200_compress", "agf2_b200_eigh", "agf2_b200_launch_count", "agf2_b200_last_kernel_ms",
-    "agf2_b200_set_simple_kernels",
+    "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap",
 ]
 
 
@@ -100,6 +100,10 @@ def last_kernel_ms():
 
 def set_simple_kernels(on):
     check(_libagf2.agf2_b200_set_simple_kernels(1 if on else 0))
+
+
+def set_overlap(on):
+    check(_libagf2.agf2_b200_set_overlap(1 if on else 0))
 
 
 def set_workspace_bytes(nbytes):

@@ -151,6 +151,10 @@ int agf2_b200_ao2mo_sector(agf2_b200_eri *h, const double *v_occ, int64_t nocc, 
 int64_t agf2_b200_launch_count(int reset);
 int agf2_b200_last_kernel_ms(double *k1_form_ms, double *k2_moment_ms);
 
+/* Chunks alternate between two CUDA streams (default on) so that the tail of one kernel is filled by the
+ * other chain's CTAs.  Switch it off to time k1_form / k2_moment in isolation (agf2_b200_last_kernel_ms). */
+int agf2_b200_set_overlap(int on);
+
 /* Debug: route the moment build through the naive one-thread-per-element CUDA kernels (same
  * planner, no tensor cores); used by the tests to separate planner bugs from kernel bugs. */
 int agf2_b200_set_simple_kernels(int on);
