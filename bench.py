@@ -121,7 +121,11 @@ def cpu_reference_sample(o, v, n, p, budget_s=20.0):
     if orc.have_ref():
         kind = "reference"
         orc.load_ref()
-        omp = int(max(1, min(cores, 24.0 // max(per_thread_gb, 1e-9), o)))
+        try:
+            avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 1e9
+        except Exception:
+            avail_gb = 32.0
+        omp = int(max(1, min(cores, (0.5 * avail_gb) // max(per_thread_gb, 1e-9), o)))
         blas = max(1, cores // omp)
         orc.ref_set_threads(omp=omp, blas=blas)
         fn = lambda i0, i1: orc.ref_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, i0, i1)  # noqa: E731
