@@ -295,6 +295,19 @@ def main():
         return 0
 
     peak, peak_src = fp64_peak()
+    traffic = None
+    try:   # DRAM bytes of one k1_form launch from the committed `ncu --set full` capture
+        import csv
+        with open(os.path.join(ROOT, "profiles", "r01_k1_form_ncu.csv")) as f:
+            m = {r[2]: (float(r[3]), r[4]) for r in csv.reader(f) if r[0] == "0"}
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
+        traffic = {"bytes_per_launch": rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]],
+                   "launch": "k1_form grid 378 (21 pole pairs of o=64 v=100 naux=4000 nphys=1100), "
+                             "operand bytes of that launch 0.85e9 (22 poles x (ixq 35.2 MB + qja 3.2 MB))",
+                   "source": "profiles/r01_k1_form_ncu.csv"}
+    except Exception:
+        pass
     k1_flops = f_k1(o, v, n, p) + f_k1(v, o, n, p)
     k1_tf = k1_flops / world / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else None
     k2_flops = flops_build - k1_flops
@@ -308,7 +321,7 @@ def main():
         "frac_of_fp64_peak": flops_build / (ms_per_step * 1e-3) * 1e-12 / (peak * world),
         "fp64_peak_tflops": peak, "fp64_peak_source": peak_src,
         "roofline": {"bound": "tensor", "kernel": "k1_form (FP64 DMMA.8x8x4)", "achieved": k1_tf, "peak": peak,
-                     "unit": "TFLOP/s", "frac": (k1_tf / peak) if k1_tf else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (k1_tf / peak) if k1_tf else None, "traffic": traffic,
                      "k1_ms_per_step": k1_ms, "k2_ms_per_step": k2_ms,
                      "note": "k1/k2 launch times from an extra untimed step with the chunk overlap off (each launch "
                              "alone on the GPU); the timed steps overlap the two kernels on two streams",
