@@ -66,6 +66,8 @@ def test_golden_uhf(lib, golden_dir, simple):
 @pytest.mark.parametrize("shape", [
     (5, 8, 40, 13), (3, 19, 37, 24), (12, 30, 100, 42), (7, 100, 130, 50), (6, 5, 16, 130),
     (24, 240, 1000, 264), (40, 100, 333, 141), (9, 65, 129, 257), (2, 7, 15, 3),
+    (5, 19, 84, 24),          # water cc-pVDZ scale (BASELINE.json configs[0]: P=24, o=5, v=19)
+    (21, 243, 680, 264),      # benzene cc-pVTZ / cc-pVTZ-RI scale, HF shape (configs[1])
 ])
 def test_parity_ladder_rhf(lib, shape):
     o, v, n, p = shape
