@@ -176,24 +176,11 @@ class OptRAGF2:
                                                                self.chempot))
 
     def get_fock(self, rdm1=None):
-        """DF Fock matrix f = h + J - K/2 from the packed DF tensor (optragf2.py:358-398), blocked over naux."""
+        """DF Fock matrix f = h + J - K/2 (optragf2.py:358-398).  J and K are built on the device from the
+        resident DF tensor (two GEMVs + blocked GEMMs) instead of the reference's host loop over naux blocks."""
         rdm1 = self.rdm1 if rdm1 is None else rdm1
-        nphys, naux = self.nphys, self.eri.shape[0]
-        maxblk = int(self.options["maxblk"])
-        il = np.tril_indices(nphys)
-        rdm1_tril = (rdm1 + np.tril(rdm1, k=-1))[il]
-        j = np.zeros(nphys * (nphys + 1) // 2)
-        k = np.zeros((nphys, nphys))
-        for p0 in range(0, naux, maxblk):
-            eri1 = self.eri[p0:p0 + maxblk]
-            j += (eri1 @ rdm1_tril) @ eri1
-            l3 = unpack_tril(eri1, nphys)
-            half = l3 @ rdm1                                  # (Q, p, r) = sum_s L[Q,p,s] D[s,r]
-            k += np.einsum("Qpr,Qqr->pq", half, l3, optimize=True)
-        jm = np.zeros((nphys, nphys))
-        jm[il] = j
-        jm = jm + jm.T - np.diag(np.diag(jm))
-        return self.h1e + jm - 0.5 * k
+        j, k = self._eri_dev.get_jk(rdm1)
+        return self.h1e + j - 0.5 * k
 
     # ---------------------------------------------------------------------------------------------
     @record_time("energy")

@@ -8,7 +8,7 @@ from auxgf_b200 import backend
 from auxgf_b200.aux import Aux, energy
 from auxgf_b200.agf2 import optragf2
 from auxgf_b200.agf2.fock import fock_loop_uhf
-from auxgf_b200.agf2.optragf2 import (OptRAGF2, allreduce_moments, dist_info, pack_tril, unpack_tril)
+from auxgf_b200.agf2.optragf2 import OptRAGF2, allreduce_moments, dist_info, pack_tril
 from auxgf_b200.util import record_energy, record_time
 
 
@@ -79,26 +79,10 @@ class OptUAGF2(OptRAGF2):
                   % (("converged" if converged else "did not converge",) + tuple(self.chempot)))
 
     def get_fock(self, rdm1=None):
+        """f_a = h_a + J_a + J_b - K_a, f_b = h_b + J_b + J_a - K_b (optuagf2.py:317-366), J/K on the device."""
         rdm1 = self.rdm1 if rdm1 is None else rdm1
-        nphys = self.nphys
-        maxblk = int(self.options["maxblk"])
-        il = np.tril_indices(nphys)
-
-        def _get_jk(d, eri):
-            d_tril = (d + np.tril(d, k=-1))[il]
-            j = np.zeros(nphys * (nphys + 1) // 2)
-            k = np.zeros((nphys, nphys))
-            for p0 in range(0, eri.shape[0], maxblk):
-                eri1 = eri[p0:p0 + maxblk]
-                j += (eri1 @ d_tril) @ eri1
-                l3 = unpack_tril(eri1, nphys)
-                k += np.einsum("Qpr,Qqr->pq", l3 @ d, l3, optimize=True)
-            jm = np.zeros((nphys, nphys))
-            jm[il] = j
-            return jm + jm.T - np.diag(np.diag(jm)), k
-
-        j_a, k_a = _get_jk(rdm1[0], self.eri[0])
-        j_b, k_b = _get_jk(rdm1[1], self.eri[1])
+        j_a, k_a = self._eri_dev[0].get_jk(rdm1[0])
+        j_b, k_b = self._eri_dev[1].get_jk(rdm1[1])
         return np.stack([self.h1e[0] + j_a + j_b - k_a, self.h1e[1] + j_b + j_a - k_b])
 
     @record_time("energy")

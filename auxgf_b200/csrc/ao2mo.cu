@@ -22,6 +22,15 @@ int afail(int code, const std::string& m) { a_err = m; return code; }
 
 cublasHandle_t a_blas = nullptr;
 
+// Lp[q][Q][s] = L[Q0 + Q][q][s] for one block of auxiliary functions (p-major copy for the exchange GEMM)
+__global__ void permute_block_kernel(const double* __restrict__ full, double* __restrict__ lp, int nphys, int nq)
+{
+    const int Q = blockIdx.z, q = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nphys) return;
+    lp[((long long)q * nq + Q) * nphys + s] = full[((long long)Q * nphys + q) * nphys + s];
+}
+
 // packed lower triangle (row p, col q <= p at p(p+1)/2 + q; pyscf.lib.pack_tril) -> full symmetric
 __global__ void unpack_tril_kernel(const double* __restrict__ packed, double* __restrict__ full, int nphys, long long npair)
 {
@@ -43,6 +52,8 @@ struct agf2_b200_eri {
     size_t qja_elems = 0;
     double* coef = nullptr;           // staged coefficient matrices
     size_t coef_elems = 0;
+    double* jk = nullptr;             // get_jk scratch: D, rho, J, K, T', L' blocks
+    size_t jk_elems = 0;
 };
 
 extern "C" const char* agf2_b200_ao2mo_last_error(void) { return a_err.c_str(); }
@@ -89,7 +100,7 @@ extern "C" int agf2_b200_eri_create(const double* eri, int64_t naux, int64_t nph
 extern "C" int agf2_b200_eri_destroy(agf2_b200_eri* h)
 {
     if (!h) return 0;
-    cudaFree(h->full); cudaFree(h->ixq); cudaFree(h->qja); cudaFree(h->coef);
+    cudaFree(h->full); cudaFree(h->ixq); cudaFree(h->qja); cudaFree(h->coef); cudaFree(h->jk);
     delete h;
     return 0;
 }
@@ -145,5 +156,50 @@ extern "C" int agf2_b200_ao2mo_sector(agf2_b200_eri* h, const double* v_occ, int
                                      &zero, h->qja, (int)(nocc * ldv), ldv, (int)nocc));
     *ixq_out = h->ixq; *ld_ixq_out = ldn;
     *qja_out = h->qja; *ld_qja_out = ldv;
+    return 0;
+}
+
+
+// Coulomb and exchange matrices from the resident DF tensor (replaces the blocked host loop of
+// auxgf/agf2/optragf2.py:358-398 / optuagf2.py:317-366):
+//     J[p,q] = sum_Q L[Q,p,q] (sum_rs L[Q,r,s] D[r,s]),     K[p,q] = sum_Q sum_rs L[Q,p,r] D[r,s] L[Q,q,s]
+// rdm1, j, k: (nphys, nphys) row-major; host or device memory (on_device).  Library GEMV/GEMMs (cuBLAS).
+extern "C" int agf2_b200_get_jk(agf2_b200_eri* h, const double* rdm1, double* j_out, double* k_out, int on_device,
+                                void* stream)
+{
+    if (!h || !rdm1 || !j_out || !k_out) return afail(AGF2_B200_EINVAL, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t P = h->nphys, N = h->naux, PP = P * P;
+    // block of auxiliary functions sized so that T' and L' stay within ~512 MiB each
+    const int64_t qblk = std::max<int64_t>(1, std::min<int64_t>(N, (int64_t)((512ll << 20) / (PP * 8))));
+    const size_t need = (size_t)(3 * PP + N + 2 * qblk * PP);
+    if (int r = agrow(h->jk, h->jk_elems, need)) return r;
+    double* D = h->jk; double* J = D + PP; double* K = J + PP; double* rho = K + PP;
+    double* Tp = rho + N; double* Lp = Tp + qblk * PP;
+    const cudaMemcpyKind in = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind out = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    A_CU(cudaMemcpyAsync(D, rdm1, (size_t)PP * 8, in, st));
+    A_CU(cudaMemsetAsync(K, 0, (size_t)PP * 8, st));
+    A_BLAS(cublasSetStream(a_blas, st));
+    const double one = 1.0, zero = 0.0;
+    // rho[Q] = sum_pq L[Q,pq] D[pq] ;  J[pq] = sum_Q rho[Q] L[Q,pq]       (L as column-major (P^2 x N))
+    A_BLAS(cublasDgemv(a_blas, CUBLAS_OP_T, (int)PP, (int)N, &one, h->full, (int)PP, D, 1, &zero, rho, 1));
+    A_BLAS(cublasDgemv(a_blas, CUBLAS_OP_N, (int)PP, (int)N, &one, h->full, (int)PP, rho, 1, &zero, J, 1));
+    for (int64_t q0 = 0; q0 < N; q0 += qblk) {
+        const int64_t nq = std::min(qblk, N - q0);
+        const double* Lb = h->full + q0 * PP;
+        // T'[p][Q][s] = sum_r L[Q,p,r] D[r,s]   (batched over p; written p-major)
+        A_BLAS(cublasDgemmStridedBatched(a_blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)P, (int)nq, (int)P, &one,
+                                         D, (int)P, 0, Lb, (int)PP, P, &zero, Tp, (int)P, nq * P, (int)P));
+        dim3 grid((unsigned)((P + 127) / 128), (unsigned)P, (unsigned)nq);
+        permute_block_kernel<<<grid, 128, 0, st>>>(Lb, Lp, (int)P, (int)nq);
+        A_CU(cudaGetLastError());
+        // K[p,q] += sum_{(Q,s)} T'[p,(Q,s)] L'[q,(Q,s)]
+        A_BLAS(cublasDgemm(a_blas, CUBLAS_OP_T, CUBLAS_OP_N, (int)P, (int)P, (int)(nq * P), &one, Lp, (int)(nq * P),
+                           Tp, (int)(nq * P), &one, K, (int)P));
+    }
+    A_CU(cudaMemcpyAsync(j_out, J, (size_t)PP * 8, out, st));
+    A_CU(cudaMemcpyAsync(k_out, K, (size_t)PP * 8, out, st));
+    A_CU(cudaStreamSynchronize(st));
     return 0;
 }

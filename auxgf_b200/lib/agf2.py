@@ -296,7 +296,9 @@ _libagf2.agf2_b200_eri_destroy.argtypes = [_vp]
 _libagf2.agf2_b200_eri_full_ptr.argtypes = [_vp, ctypes.POINTER(_vp)]
 _libagf2.agf2_b200_ao2mo_sector.argtypes = [_vp, _vp, _i64, _vp, _i64, ctypes.c_int, _vp, ctypes.POINTER(_vp),
                                             ctypes.POINTER(_i64), ctypes.POINTER(_vp), ctypes.POINTER(_i64)]
-SYMBOLS += ["agf2_b200_eri_create", "agf2_b200_eri_destroy", "agf2_b200_eri_full_ptr", "agf2_b200_ao2mo_sector"]
+_libagf2.agf2_b200_get_jk.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, _vp]
+SYMBOLS += ["agf2_b200_eri_create", "agf2_b200_eri_destroy", "agf2_b200_eri_full_ptr", "agf2_b200_ao2mo_sector",
+            "agf2_b200_get_jk"]
 
 
 def _check2(status):
@@ -353,6 +355,13 @@ class DeviceERI:
                                                 v_vir.shape[1], 0, self._stream(), ctypes.byref(ixq),
                                                 ctypes.byref(ldi), ctypes.byref(qja), ctypes.byref(ldq)))
         return ixq.value, ldi.value, qja.value, ldq.value
+
+    def get_jk(self, rdm1):
+        """J, K (host arrays) of a host density matrix, built on the device from the resident DF tensor."""
+        rdm1 = _c(rdm1, 2)
+        j = np.empty_like(rdm1); k = np.empty_like(rdm1)
+        _check2(_libagf2.agf2_b200_get_jk(self._h, rdm1.ctypes.data, j.ctypes.data, k.ctypes.data, 0, self._stream()))
+        return j, k
 
     def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
         """vv, vev (CUDA tensors) of one sector, everything on the device."""

@@ -146,6 +146,11 @@ int agf2_b200_ao2mo_sector(agf2_b200_eri *h, const double *v_occ, int64_t nocc, 
                            int64_t nvir, int on_device, void *stream, double **ixq, int64_t *ld_ixq,
                            double **qja, int64_t *ld_qja);
 
+/* Coulomb / exchange matrices of a density from the resident DF tensor (replaces the blocked host loop
+ * of auxgf/agf2/optragf2.py:358-398, optuagf2.py:317-366):  J = sum_Q L_Q tr(L_Q D),  K = sum_Q L_Q D L_Q.
+ * rdm1, j, k: (nphys, nphys) row-major, host or device (on_device); blocking call. */
+int agf2_b200_get_jk(agf2_b200_eri *h, const double *rdm1, double *j, double *k, int on_device, void *stream);
+
 /* Instrumentation: number of kernels launched by this library since the last reset, and the
  * device time (ms, CUDA events) of the last moments call's two kernels summed over launches. */
 int64_t agf2_b200_launch_count(int reset);

@@ -21,6 +21,13 @@ class _HostERI:
     def sector(self, v_occ, v_vir):
         return self._blocks(v_occ, v_vir)
 
+    def get_jk(self, rdm1):
+        """optragf2.py:358-398 restated with einsum."""
+        rho = np.einsum("Qpq,pq->Q", self.full, rdm1)
+        j = np.einsum("Q,Qpq->pq", rho, self.full)
+        k = np.einsum("Qpr,rs,Qqs->pq", self.full, rdm1, self.full, optimize=True)
+        return j, k
+
     def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
         o, v, p = gf_occ.naux, gf_vir.naux, self.nphys
         ixq, qja = self._blocks(gf_occ.v, gf_vir.v)

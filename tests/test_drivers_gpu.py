@@ -67,6 +67,20 @@ def test_device_ao2mo_matches_oracle():
     eri.close()
 
 
+def test_device_jk_matches_oracle():
+    from auxgf_b200.lib import agf2 as lib
+    rng = np.random.default_rng(1)
+    n, p = 45, 33
+    l3 = rng.standard_normal((n, p, p)); l3 = l3 + l3.transpose(0, 2, 1)
+    d = rng.standard_normal((p, p)); d = d + d.T
+    eri = lib.DeviceERI(l3, p, packed=False)
+    j, k = eri.get_jk(d)
+    rj = np.einsum("Qpq,Qrs,rs->pq", l3, l3, d, optimize=True)
+    rk = np.einsum("Qpr,rs,Qqs->pq", l3, d, l3, optimize=True)
+    assert relerr(j, rj) < 1e-12 and relerr(k, rk) < 1e-12
+    eri.close()
+
+
 def test_optragf2_cuda_vs_oracle():
     hf = ModelRHF(nao=24, nocc=5, naux=70, seed=1).run()
     g, e0 = _run("OptRAGF2", hf, 3)
