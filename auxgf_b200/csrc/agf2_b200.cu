@@ -13,11 +13,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/agf2_b200.h"
@@ -63,6 +65,8 @@ struct Ctx {
     size_t e_elems[2] = {0, 0};
     bool overlap = true;               // odd chunks run on a second stream: one chain's tail is filled by the other
     cudaStream_t stream2 = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> pole_ev;
     cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr}, ev_start = nullptr;
     double* acc = nullptr;   // 4 accumulators: S_vv, S_vev, A_vv, A_vev
     size_t acc_elems = 0;
@@ -114,6 +118,7 @@ int ensure_ctx() {
     }
     CU_TRY(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
     CU_TRY(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
     if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
@@ -155,6 +160,16 @@ struct SubTile { int i, j, a0, nb, bsel, esel, nv; long long col; double p, eij;
 
 inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Host-pointer API only: ixq is uploaded pole by pole on a copy stream by a helper thread while the GPU
+// already works on the pairs whose poles have landed.  rank[i] = position of pole i in the upload order,
+// ev[k] is recorded after the k-th upload, ready = number of uploads whose event has been recorded.
+struct PoleGate {
+    const std::vector<int>* rank;
+    const std::vector<cudaEvent_t>* ev;
+    std::atomic<int>* ready;
+    std::atomic<int>* failed;
+};
+
 void record(cudaStream_t st, int kind, bool begin) {
     Ctx& c = g_ctx;
     if (!c.profile) return;
@@ -177,7 +192,7 @@ void record(cudaStream_t st, int kind, bool begin) {
 int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other,
                 const double* ei_same_host, const double* ei_other_host, int64_t nphys, int64_t naux,
                 int64_t istart, int64_t iend, double c_same, double s_same, double os_other, int64_t part,
-                int64_t nparts, double* vv, double* vev, cudaStream_t st)
+                int64_t nparts, double* vv, double* vev, cudaStream_t st, const PoleGate* gate = nullptr)
 {
     Ctx& c = g_ctx;
     const int64_t o = same.nocc, v = same.nvir;
@@ -297,11 +312,16 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             tiles.clear();
             plain.clear();
             int64_t col = 0;
+            int need_rank = -1;
             while (pos < items.size()) {
                 const Item& it = items[pos];
                 const int64_t w = it.kind == 2 ? vbpad : vpad;
                 const int nblk = it.kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
                 if (col + nblk * w > cap_cols) break;
+                if (gate) {
+                    need_rank = std::max(need_rank, (*gate->rank)[it.i]);
+                    if (it.kind != 2) need_rank = std::max(need_rank, (*gate->rank)[it.j]);
+                }
                 if (it.kind == 1 || it.kind == 3) {
                     const double eij = ei_same_host[it.i] + ei_same_host[it.j];
                     const long long c1 = col, c2 = (it.kind == 1 && ca != 0.0) ? col + w : col;
@@ -390,6 +410,14 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             memcpy(c.h_t1[buf], tiles.data(), tiles.size() * sizeof(K1Tile));
             CU_TRY(cudaMemcpyAsync(c.d_t1[buf], c.h_t1[buf], tiles.size() * sizeof(K1Tile), cudaMemcpyHostToDevice, sc));
 
+            // ---- host-pointer API: wait until the poles of this chunk have been uploaded ----
+            if (gate && need_rank >= 0) {
+                while (gate->ready->load(std::memory_order_acquire) <= need_rank) {
+                    if (gate->failed->load()) return fail(AGF2_B200_ECUDA, "ixq upload failed");
+                    std::this_thread::yield();
+                }
+                CU_TRY(cudaStreamWaitEvent(sc, (*gate->ev)[need_rank], 0));
+            }
             // ---- K1: form the integral blocks of this chunk ----
             double* const Wa = c.W[buf][0];
             double* const Wb = c.W[buf][1];
@@ -478,6 +506,51 @@ int stage_in(int slot, const double* host, int64_t rows, int64_t cols, int64_t* 
     return 0;
 }
 
+// Pipelined upload of ixq (nocc poles of nphys x naux) for the host-pointer API.
+struct Uploader {
+    std::thread th;
+    std::atomic<int> ready{0}, failed{0};
+    std::vector<int> rank;
+    PoleGate g;
+
+    int start(const double* host, int slot, int64_t nocc, int64_t nphys, int64_t naux, int64_t istart, int64_t iend,
+              int64_t* ld_out) {
+        Ctx& c = g_ctx;
+        const int64_t ld = rup(naux, 2);
+        if (int r = grow(c.stage[slot], c.stage_elems[slot], (size_t)std::max<int64_t>(nocc * nphys * ld, 2), false)) return r;
+        *ld_out = ld;
+        while ((int64_t)c.pole_ev.size() < nocc) {
+            cudaEvent_t e;
+            CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c.pole_ev.push_back(e);
+        }
+        std::vector<int> order;
+        for (int64_t i = istart; i < iend; ++i) order.push_back((int)i);      // the poles the pair loop needs first
+        for (int64_t i = 0; i < istart; ++i) order.push_back((int)i);
+        for (int64_t i = iend; i < nocc; ++i) order.push_back((int)i);
+        rank.assign((size_t)nocc, 0);
+        for (size_t k = 0; k < order.size(); ++k) rank[order[k]] = (int)k;
+        g.rank = &rank; g.ev = &c.pole_ev; g.ready = &ready; g.failed = &failed;
+        double* dev = c.stage[slot];
+        const int device = c.device;
+        cudaStream_t cs = c.copy_stream;
+        th = std::thread([=]() {
+            if (cudaSetDevice(device) != cudaSuccess) { failed.store(1); return; }
+            for (size_t k = 0; k < order.size(); ++k) {
+                const int64_t i = order[k];
+                cudaError_t e = cudaMemcpy2DAsync(dev + i * nphys * ld, ld * 8, host + i * nphys * naux, naux * 8,
+                                                  naux * 8, nphys, cudaMemcpyHostToDevice, cs);
+                if (e == cudaSuccess) e = cudaEventRecord(g_ctx.pole_ev[k], cs);
+                if (e != cudaSuccess) { failed.store(1); return; }
+                ready.store((int)k + 1, std::memory_order_release);
+            }
+        });
+        return 0;
+    }
+    void join() { if (th.joinable()) th.join(); }
+    ~Uploader() { join(); }
+};
+
 }  // namespace
 
 // =================================================================================================
@@ -520,10 +593,10 @@ int agf2_b200_last_kernel_ms(double* k1, double* k2) {
     return 0;
 }
 
-int agf2_b200_moments_rhf_dev(const double* ixq, int64_t ld_ixq, const double* qja, int64_t ld_qja, const double* ei,
-                              const double* ea, int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux,
-                              int64_t istart, int64_t iend, double os_factor, double ss_factor, int64_t part,
-                              int64_t nparts, double* vv, double* vev, void* stream, int sync)
+static int moments_rhf_impl(const double* ixq, int64_t ld_ixq, const double* qja, int64_t ld_qja, const double* ei,
+                            const double* ea, int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux,
+                            int64_t istart, int64_t iend, double os_factor, double ss_factor, int64_t part,
+                            int64_t nparts, double* vv, double* vev, void* stream, int sync, const PoleGate* gate)
 {
     if (int r = ensure_ctx()) return r;
     if (!ixq || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
@@ -535,18 +608,27 @@ int agf2_b200_moments_rhf_dev(const double* ixq, int64_t ld_ixq, const double* q
     Spin same;
     same.qja = qja; same.ld = ld_qja; same.nocc = nocc; same.nvir = nvir; same.ea_dev = ea;
     int r = run_moments(ixq, ld_ixq, same, nullptr, ei_h.data(), nullptr, nphys, naux, istart, iend,
-                        os_factor + ss_factor, ss_factor, 0.0, part, nparts, vv, vev, st);
+                        os_factor + ss_factor, ss_factor, 0.0, part, nparts, vv, vev, st, gate);
     if (r) return r;
     if (sync) return finish_profile(st);
     return 0;
 }
 
-int agf2_b200_moments_uhf_dev(const double* ixq_a, int64_t ld_ixq, const double* qja_a, int64_t ld_qja_a,
-                              const double* qja_b, int64_t ld_qja_b, const double* ei_a, const double* ei_b,
-                              const double* ea_a, const double* ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
-                              int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart, int64_t iend,
-                              double os_factor, double ss_factor, int64_t part, int64_t nparts, double* vv,
-                              double* vev, void* stream, int sync)
+int agf2_b200_moments_rhf_dev(const double* ixq, int64_t ld_ixq, const double* qja, int64_t ld_qja, const double* ei,
+                              const double* ea, int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux,
+                              int64_t istart, int64_t iend, double os_factor, double ss_factor, int64_t part,
+                              int64_t nparts, double* vv, double* vev, void* stream, int sync)
+{
+    return moments_rhf_impl(ixq, ld_ixq, qja, ld_qja, ei, ea, nphys, nocc, nvir, naux, istart, iend, os_factor,
+                            ss_factor, part, nparts, vv, vev, stream, sync, nullptr);
+}
+
+static int moments_uhf_impl(const double* ixq_a, int64_t ld_ixq, const double* qja_a, int64_t ld_qja_a,
+                            const double* qja_b, int64_t ld_qja_b, const double* ei_a, const double* ei_b,
+                            const double* ea_a, const double* ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                            int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart, int64_t iend,
+                            double os_factor, double ss_factor, int64_t part, int64_t nparts, double* vv,
+                            double* vev, void* stream, int sync, const PoleGate* gate)
 {
     if (int r = ensure_ctx()) return r;
     if (!ixq_a || !qja_a || !ei_a || !ea_a || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
@@ -563,10 +645,22 @@ int agf2_b200_moments_uhf_dev(const double* ixq_a, int64_t ld_ixq, const double*
     other.qja = qja_b; other.ld = ld_qja_b; other.nocc = nocc_b; other.nvir = nvir_b; other.ea_dev = ea_b;
     // same-spin: Coulomb ss, exchange ss (optuagf2.c:211-256); opposite spin: Coulomb os
     int r = run_moments(ixq_a, ld_ixq, same, has_b ? &other : nullptr, eia.data(), eib.data(), nphys, naux, istart,
-                        iend, ss_factor, ss_factor, os_factor, part, nparts, vv, vev, st);
+                        iend, ss_factor, ss_factor, os_factor, part, nparts, vv, vev, st, gate);
     if (r) return r;
     if (sync) return finish_profile(st);
     return 0;
+}
+
+int agf2_b200_moments_uhf_dev(const double* ixq_a, int64_t ld_ixq, const double* qja_a, int64_t ld_qja_a,
+                              const double* qja_b, int64_t ld_qja_b, const double* ei_a, const double* ei_b,
+                              const double* ea_a, const double* ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                              int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart, int64_t iend,
+                              double os_factor, double ss_factor, int64_t part, int64_t nparts, double* vv,
+                              double* vev, void* stream, int sync)
+{
+    return moments_uhf_impl(ixq_a, ld_ixq, qja_a, ld_qja_a, qja_b, ld_qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a,
+                            nocc_b, nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor, part, nparts, vv, vev,
+                            stream, sync, nullptr);
 }
 
 int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const double* ei, const double* ea,
@@ -580,7 +674,6 @@ int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const do
     Ctx& c = g_ctx;
     cudaStream_t st = c.stream;
     int64_t ld_ixq, ld_qja, ld1;
-    if (int r = stage_in(0, ixq, nocc * nphys, naux, &ld_ixq, st)) return r;
     if (int r = stage_in(1, qja, naux * nocc, nvir, &ld_qja, st)) return r;   // (naux*nocc) rows of nvir
     if (int r = stage_in(2, ei, 1, nocc, &ld1, st)) return r;
     if (int r = stage_in(3, ea, 1, nvir, &ld1, st)) return r;
@@ -588,8 +681,11 @@ int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const do
     CU_TRY(cudaMemsetAsync(c.stage[4], 0, (size_t)2 * nphys * nphys * 8, st));
     double* dvv = c.stage[4];
     double* dvev = c.stage[4] + nphys * nphys;
-    int r = agf2_b200_moments_rhf_dev(c.stage[0], ld_ixq, c.stage[1], ld_qja, c.stage[2], c.stage[3], nphys, nocc, nvir,
-                                      naux, istart, iend, os_factor, ss_factor, 0, 1, dvv, dvev, st, 1);
+    Uploader up;      // ixq streams in pole by pole while the first pairs are already being processed
+    if (int r = up.start(ixq, 0, nocc, nphys, naux, istart, iend, &ld_ixq)) return r;
+    int r = moments_rhf_impl(c.stage[0], ld_ixq, c.stage[1], ld_qja, c.stage[2], c.stage[3], nphys, nocc, nvir,
+                             naux, istart, iend, os_factor, ss_factor, 0, 1, dvv, dvev, st, 1, &up.g);
+    up.join();
     if (r) return r;
     std::vector<double> h((size_t)2 * nphys * nphys);
     CU_TRY(cudaMemcpy(h.data(), c.stage[4], h.size() * 8, cudaMemcpyDeviceToHost));
@@ -612,7 +708,6 @@ int agf2_b200_build_part_loop_uhf(const double* ixq_a, const double* qja_a, cons
     cudaStream_t st = c.stream;
     const bool has_b = nocc_b > 0 && nvir_b > 0;
     int64_t ld_ixq, ld_qa, ld_qb = 2, ld1;
-    if (int r = stage_in(0, ixq_a, nocc_a * nphys, naux, &ld_ixq, st)) return r;
     if (int r = stage_in(1, qja_a, naux * nocc_a, nvir_a, &ld_qa, st)) return r;
     if (int r = stage_in(2, ei_a, 1, nocc_a, &ld1, st)) return r;
     if (int r = stage_in(3, ea_a, 1, nvir_a, &ld1, st)) return r;
@@ -625,10 +720,13 @@ int agf2_b200_build_part_loop_uhf(const double* ixq_a, const double* qja_a, cons
     CU_TRY(cudaMemsetAsync(c.stage[4], 0, (size_t)2 * nphys * nphys * 8, st));
     double* dvv = c.stage[4];
     double* dvev = c.stage[4] + nphys * nphys;
-    int r = agf2_b200_moments_uhf_dev(c.stage[0], ld_ixq, c.stage[1], ld_qa, has_b ? c.stage[5] : nullptr, ld_qb,
-                                      c.stage[2], has_b ? c.stage[6] : nullptr, c.stage[3], has_b ? c.stage[7] : nullptr,
-                                      nphys, nocc_a, has_b ? nocc_b : 0, nvir_a, has_b ? nvir_b : 0, naux, istart, iend,
-                                      os_factor, ss_factor, 0, 1, dvv, dvev, st, 1);
+    Uploader up;
+    if (int r = up.start(ixq_a, 0, nocc_a, nphys, naux, istart, iend, &ld_ixq)) return r;
+    int r = moments_uhf_impl(c.stage[0], ld_ixq, c.stage[1], ld_qa, has_b ? c.stage[5] : nullptr, ld_qb,
+                             c.stage[2], has_b ? c.stage[6] : nullptr, c.stage[3], has_b ? c.stage[7] : nullptr,
+                             nphys, nocc_a, has_b ? nocc_b : 0, nvir_a, has_b ? nvir_b : 0, naux, istart, iend,
+                             os_factor, ss_factor, 0, 1, dvv, dvev, st, 1, &up.g);
+    up.join();
     if (r) return r;
     std::vector<double> h((size_t)2 * nphys * nphys);
     CU_TRY(cudaMemcpy(h.data(), c.stage[4], h.size() * 8, cudaMemcpyDeviceToHost));
