@@ -63,6 +63,9 @@ struct Ctx {
     size_t w_elems = 0;
     double* E[2] = {nullptr, nullptr};
     size_t e_elems[2] = {0, 0};
+    bool lpt_order = true;             // k1_form tiles of a chunk launched longest first
+    bool balanced_blocks = false;      // column blocks of an item of nearly equal width (measured: no better than 64 + rest with LPT)
+    bool tune_chunk = true;            // chunk size chosen for whole waves of k1_form tiles
     bool overlap = true;               // odd chunks run on a second stream: one chain's tail is filled by the other
     cudaStream_t stream2 = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -122,6 +125,9 @@ int ensure_ctx() {
     if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
     if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_LPT")) c.lpt_order = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_BALANCED")) c.balanced_blocks = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_TUNE_CHUNK")) c.tune_chunk = atoi(e) != 0;
     c.init = true;
     return 0;
 }
@@ -186,6 +192,54 @@ void record(cudaStream_t st, int kind, bool begin) {
         cudaEventRecord(c.events[c.events_used].b, st);
         c.events_used++;
     }
+}
+
+// Column blocks (a0, nb) of one item of padded width w: ceil(w/64) blocks of nearly equal width (in units of
+// 8 columns), e.g. 104 -> 56 + 48 rather than 64 + 40, so that the CTA tiles of a launch have similar durations.
+std::vector<std::pair<int, int>> split_blocks(int64_t w, bool balanced) {
+    std::vector<std::pair<int, int>> out;
+    const int units = (int)(w / 8);
+    const int nblk = (units + 7) / 8;
+    int a0 = 0;
+    for (int b = 0; b < nblk; ++b) {
+        int nb = balanced ? units / nblk + (b < units % nblk ? 1 : 0) : std::min(8, units - 8 * b);
+        out.push_back({a0, nb});
+        a0 += 8 * nb;
+    }
+    return out;
+}
+
+// Greedy in-order dispatch of CTA tiles (durations in units of one 8-column block) over nsm SMs: the time the
+// last SM finishes.  This is how the hardware block scheduler hands out the CTAs of one k1_form launch.
+double dispatch_makespan(const std::vector<double>& durs, int nsm) {
+    std::vector<double> h((size_t)nsm, 0.0);   // min-heap of SM finish times
+    auto cmp = [](double a, double b) { return a > b; };
+    for (double d : durs) {
+        std::pop_heap(h.begin(), h.end(), cmp);
+        h.back() += d;
+        std::push_heap(h.begin(), h.end(), cmp);
+    }
+    return *std::max_element(h.begin(), h.end());
+}
+
+// How many identical work items one chunk should hold (<= n_max, what the workspace allows) so that the tiles
+// of the k1_form launch fill an integer number of waves: maximises work / (makespan + launch overhead).
+int pick_chunk_items(const std::vector<double>& item_tiles, int n_max, int nsm, bool lpt, double launch_ovh) {
+    if (n_max <= 1) return 1;
+    int best_n = n_max;
+    double best = -1.0;
+    const int lo = std::max(1, n_max / 2), step = std::max(1, (n_max - lo) / 48);
+    double per_item = 0.0;
+    for (double d : item_tiles) per_item += d;
+    for (int n = n_max; n >= lo; n -= step) {
+        std::vector<double> durs;
+        durs.reserve(item_tiles.size() * (size_t)n);
+        for (int k = 0; k < n; ++k) durs.insert(durs.end(), item_tiles.begin(), item_tiles.end());
+        if (lpt) std::stable_sort(durs.begin(), durs.end(), [](double a, double b) { return a > b; });
+        const double eff = per_item * n / nsm / (dispatch_makespan(durs, nsm) + launch_ovh);
+        if (eff > best * 1.005) { best = eff; best_n = n; }   // prefer the larger chunk unless clearly worse
+    }
+    return best_n;
 }
 
 // The whole moment build on device-resident inputs.
@@ -273,20 +327,57 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     const int nk1 = (int)((naux + kKB - 1) / kKB);
 
     // ---- items of this part -----------------------------------------------------------------------
+    // (kinds are kept contiguous -- PAIR, then DIAG, then OS -- so that the chunks are homogeneous and their
+    // size can be tuned to whole waves of CTA tiles; within a kind the order is i-major, which is also the
+    // order in which the host-pointer API uploads the poles)
     std::vector<Item> sym_items, asym_items;
     {
         int64_t n_diag = 0, n_pair = 0, n_os = 0, n_asym = 0;
+        std::vector<Item> diag_items, os_items;
         for (int64_t i = istart; i < iend; ++i) {
-            if (cd != 0.0 && (n_diag++ % nparts) == part) sym_items.push_back({0, (int)i, (int)i});
+            if (cd != 0.0 && (n_diag++ % nparts) == part) diag_items.push_back({0, (int)i, (int)i});
             for (int64_t j = istart; j < i; ++j)
                 if ((n_pair++ % nparts) == part) sym_items.push_back({1, (int)i, (int)j});
             if (other && co != 0.0)
                 for (int64_t J = 0; J < other->nocc; ++J)
-                    if ((n_os++ % nparts) == part) sym_items.push_back({2, (int)i, (int)J});
+                    if ((n_os++ % nparts) == part) os_items.push_back({2, (int)i, (int)J});
             for (int64_t j = 0; j < o; ++j)
                 if ((j < istart || j >= iend) && (n_asym++ % nparts) == part) asym_items.push_back({3, (int)i, (int)j});
         }
+        sym_items.insert(sym_items.end(), diag_items.begin(), diag_items.end());
+        sym_items.insert(sym_items.end(), os_items.begin(), os_items.end());
     }
+    const std::vector<std::pair<int, int>> blk_same = split_blocks(vpad, c.balanced_blocks);
+    const std::vector<std::pair<int, int>> blk_other = split_blocks(vbpad, c.balanced_blocks);
+    // items per chunk, per kind (0 = not yet chosen)
+    int chunk_items[4] = {0, 0, 0, 0};
+    auto items_per_chunk = [&](int kind) -> int {
+        if (chunk_items[kind]) return chunk_items[kind];
+        const int64_t w = kind == 2 ? vbpad : vpad;
+        const int nblk = kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
+        const int n_max = (int)std::max<int64_t>(1, cap_cols / std::max<int64_t>(1, nblk * w));
+        int n = n_max;
+        if (c.tune_chunk && !c.simple) {
+            // tile durations of one item, in 8-column units; ~0.15 units of fill + epilogue per tile at nk = 250
+            const double ovh = 0.15 * 250.0 / std::max(1, (int)((naux + kKB - 1) / kKB));
+            std::vector<double> t;
+            const auto& blks = kind == 2 ? blk_other : blk_same;
+            if (kind == 1 || kind == 3) {
+                for (int xb = 0; xb < nxb; ++xb)
+                    for (auto& b : blks) t.push_back(2.0 * b.second + ovh);
+            } else {
+                // plain blocks pair up two by two across items: model one item as half-tiles
+                for (int xb = 0; xb < nxb; ++xb)
+                    for (auto& b : blks) t.push_back(b.second + 0.5 * ovh);
+            }
+            n = pick_chunk_items(t, n_max, c.num_sms, c.lpt_order, 0.5);
+        }
+        chunk_items[kind] = n;
+        if (getenv("AGF2_B200_VERBOSE"))
+            fprintf(stderr, "agf2_b200: kind %d: %d items per chunk (workspace allows %d), %d column blocks/item\n", kind, n,
+                    n_max, (int)(kind == 2 ? blk_other : blk_same).size());
+        return n;
+    };
 
     // K2 tile lists (upper-triangle for symmetric chunks, all tiles for non-symmetric ones)
     std::vector<K2Tile> t2_sym, t2_all;
@@ -313,7 +404,8 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             plain.clear();
             int64_t col = 0;
             int need_rank = -1;
-            while (pos < items.size()) {
+            const size_t pos_end = std::min(items.size(), pos + (size_t)items_per_chunk(items[pos].kind));
+            while (pos < pos_end) {
                 const Item& it = items[pos];
                 const int64_t w = it.kind == 2 ? vbpad : vpad;
                 const int nblk = it.kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
@@ -328,8 +420,9 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                     // tile order (pair, x-block, a-block): consecutive CTAs share the ixq rows of their
                     // x-block and the (Q|ja) columns of their pair while those are still in L2
                     for (int xb = 0; xb < nxb; ++xb) {
-                        for (int64_t a0 = 0; a0 < vpad; a0 += kTileN) {
-                            const int nb = (int)std::min<int64_t>(8, (vpad - a0) / 8);
+                        for (const auto& blk : blk_same) {
+                            const int64_t a0 = blk.first;
+                            const int nb = blk.second;
                             const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, v - a0));
                             K1Tile t;
                             memset(&t, 0, sizeof(t));
@@ -352,8 +445,9 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                     const bool os = it.kind == 2;
                     const int64_t vv_ = os ? other->nvir : v;
                     const double eij = ei_same_host[it.i] + (os ? ei_other_host[it.j] : ei_same_host[it.j]);
-                    for (int64_t a0 = 0; a0 < w; a0 += kTileN) {
-                        const int nb = (int)std::min<int64_t>(8, (w - a0) / 8);
+                    for (const auto& blk : (os ? blk_other : blk_same)) {
+                        const int64_t a0 = blk.first;
+                        const int nb = blk.second;
                         const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, vv_ - a0));
                         plain.push_back({it.i, it.j, (int)a0, nb, os ? 1 : 0, os ? 1 : 0, nv, (long long)(col + a0),
                                          os ? co : cd, eij});
@@ -384,6 +478,10 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                     tiles.push_back(t);
                 }
             }
+            // longest tiles first: the block scheduler then packs the short ones into the tail of the launch
+            if (c.lpt_order)
+                std::stable_sort(tiles.begin(), tiles.end(),
+                                 [](const K1Tile& a, const K1Tile& b) { return a.nb1 + a.nb2 > b.nb1 + b.nb2; });
 
             // ---- upload the tile list (double-buffered pinned staging) ----
             const int buf = (int)(chunk_idx & 1);
