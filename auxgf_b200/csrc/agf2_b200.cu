@@ -11,6 +11,7 @@
 //   column blocks fit the L2-sized workspace; per chunk: k1_form (integrals -> W), k2_moment (W -> vv, vev).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cublas_v2.h>
 
 #include <algorithm>
 #include <atomic>
@@ -79,6 +80,20 @@ struct Ctx {
     cudaEvent_t t1_free[2] = {nullptr, nullptr};
     K2Tile* d_t2 = nullptr;
     size_t t2_cap = 0;
+    int* d_cost = nullptr;             // stream-K cost prefixes of the K2 tile lists
+    size_t cost_cap = 0;
+    // Coulomb factorisation scratch: M = [M0 | M1], T = ixq_batch . M, per-column weights
+    bool coulomb = true;               // Coulomb factorisation allowed ...
+    bool coulomb_auto = true;          // ... and chosen per call by a flop estimate (false: always when allowed)
+    int k2_mask = 1;                   // edge tiles of k2_moment skip the column blocks they do not need
+    cublasHandle_t blas = nullptr;
+    double* Mbuf = nullptr; size_t m_elems = 0;
+    double* Tbuf[2] = {nullptr, nullptr}; size_t t_elems[2] = {0, 0};
+    double* wq[2] = {nullptr, nullptr}; size_t wq_elems[2] = {0, 0};     // w0 | w1 of the M build
+    double* we[2] = {nullptr, nullptr}; size_t we_elems[2] = {0, 0};     // e_i per (i, Q) column of a T batch
+    K2Tile* d_tm = nullptr; size_t tm_cap = 0;                           // tile list of the M build
+    int* d_cm = nullptr; size_t cm_cap = 0;
+
     // staging for the host-pointer API
     double* stage[8] = {nullptr};
     size_t stage_elems[8] = {0};
@@ -87,7 +102,7 @@ struct Ctx {
     int64_t chunk_counter = 0;
     std::vector<EventPair> events;
     size_t events_used = 0;
-    double last_ms[2] = {0, 0};
+    double last_ms[4] = {0, 0, 0, 0};   // k1_form, k2_moment (pairs), M build, Coulomb step (DGEMM + k2)
 };
 Ctx g_ctx;
 
@@ -113,7 +128,9 @@ int ensure_ctx() {
         return fail(AGF2_B200_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
     c.encode = reinterpret_cast<EncodeTiledFn>(fn);
     CU_TRY(cudaFuncSetAttribute(k1_form, cudaFuncAttributeMaxDynamicSharedMemorySize, kK1SmemBytes));
-    CU_TRY(cudaFuncSetAttribute(k2_moment, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k2_moment<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k2_moment<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    CU_TRY(cudaFuncSetAttribute(k2_moment<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytesDual));
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaEventCreateWithFlags(&c.t1_free[b], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c.ev_k1[b], cudaEventDisableTiming));
@@ -128,6 +145,9 @@ int ensure_ctx() {
     if (const char* e = getenv("AGF2_B200_LPT")) c.lpt_order = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_BALANCED")) c.balanced_blocks = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_TUNE_CHUNK")) c.tune_chunk = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_COULOMB")) { c.coulomb = atoi(e) != 0; c.coulomb_auto = atoi(e) == 2; }
+    if (const char* e = getenv("AGF2_B200_K2_MASK")) c.k2_mask = atoi(e) != 0;
+    if (cublasCreate(&c.blas) != CUBLAS_STATUS_SUCCESS) return fail(AGF2_B200_ESOLVER, "cublasCreate failed");
     c.init = true;
     return 0;
 }
@@ -159,6 +179,7 @@ struct Spin {            // one (Q|ja) tensor and its energies
     int64_t ld = 0, nocc = 0, nvir = 0;
     const double* ei = nullptr;   // host copies of the energies (planner needs e_i + e_j)
     const double* ea_dev = nullptr;
+    const double* ei_dev = nullptr;
 };
 
 struct Item { int kind, i, j; };   // kind: 0 DIAG, 1 PAIR, 2 OS, 3 ASYM
@@ -242,6 +263,148 @@ int pick_chunk_items(const std::vector<double>& item_tiles, int n_max, int nsm, 
     return best_n;
 }
 
+struct K2Launch {
+    CUtensorMap a0, a1, b;
+    K2Params p;
+    int mode;          // 0: moments (W W^T), 1: M build (two weight vectors), 2: Coulomb step (two A operands)
+    int total_cost;    // cost_prefix[ntiles]
+};
+
+int launch_k2(const K2Launch& L, cudaStream_t st) {
+    Ctx& c = g_ctx;
+    // stream-K grid: one CTA per SM, unless the launch is too small to give each >= 8 iterations
+    const long long total_it = (long long)L.total_cost * L.p.nk_inner * L.p.n_outer / 16;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c.num_sms, total_it / 8));
+    if (L.mode == 0) k2_moment<false, false><<<grid, kThreads, kK2SmemBytes, st>>>(L.a0, L.a1, L.b, L.p);
+    else if (L.mode == 1) k2_moment<false, true><<<grid, kThreads, kK2SmemBytes, st>>>(L.a0, L.a1, L.b, L.p);
+    else k2_moment<true, false><<<grid, kThreads, kK2SmemBytesDual, st>>>(L.a0, L.a1, L.b, L.p);
+    CU_TRY(cudaGetLastError());
+    c.launches++;
+    return 0;
+}
+
+// Coulomb part of the moments without forming a single Coulomb integral:
+//     sum_{i in slice} sum_{j,a} w_j X_ij X_ij^T (e_i + e_j - e_a)^n  =  sum_i ixq_i (e_i^n M0 + n M1) ixq_i^T ,
+//     M0 = sum_ja w_j q_ja q_ja^T ,  M1 = sum_ja w_j (e_j - e_a) q_ja q_ja^T      (naux x naux)
+// (k2_moment<false,true> on the (Q|ja) tensor), T = ixq_batch [M0 | M1] (cuBLAS DGEMM) and
+// k2_moment<true,false>: vv += T0 ixq^T, vev += (e_i T0 + T1) ixq^T, upper triangle only.  With nparts GPUs each
+// one owns a block of columns Q' of M (and the matching K range of the last step).
+int run_coulomb(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other, int64_t nphys, int64_t naux,
+                int64_t istart, int64_t iend, double w_same_in, double w_same_out, double w_other, int64_t part,
+                int64_t nparts, double* S_vv, double* S_vev, int64_t p_pad, const K2Tile* d_t2_sym,
+                const int* d_cost_sym, int nt_sym, int cost_sym, cudaStream_t st)
+{
+    Ctx& c = g_ctx;
+    struct Pass { const Spin* sp; double w_in, w_out; };
+    std::vector<Pass> passes;
+    const bool partial = istart > 0 || iend < same.nocc;
+    if (w_same_in != 0.0 || (partial && w_same_out != 0.0)) passes.push_back({&same, w_same_in, w_same_out});
+    if (other && w_other != 0.0) passes.push_back({other, w_other, w_other});
+    if (passes.empty() || iend <= istart) return 0;
+    const int64_t ntq = (naux + kTileN - 1) / kTileN;
+    const int64_t q_lo = ntq * part / nparts * kTileN;
+    const int64_t q_hi = std::min<int64_t>(naux, ntq * (part + 1) / nparts * kTileN);
+    if (q_hi <= q_lo) return 0;
+    const int64_t nq = q_hi - q_lo, nq_pad = rup(nq, kTileN);
+    const int64_t n_pad = rup(naux, kTileM);
+    const int64_t ldm = 2 * nq_pad;
+
+    // ---- M build ------------------------------------------------------------------------------------
+    { int r = grow(c.Mbuf, c.m_elems, (size_t)n_pad * ldm, false); if (r) return r; }
+    CU_TRY(cudaMemsetAsync(c.Mbuf, 0, (size_t)n_pad * ldm * 8, st));
+    const int nxm = (int)(n_pad / kTileM), nym = (int)(nq_pad / kTileN);
+    const int msym = (nparts == 1) ? 1 : 0;   // the whole (symmetric) M: upper-triangle tiles, mirrored afterwards
+    std::vector<K2Tile> tm;
+    std::vector<int> cm(1, 0);
+    for (int xb = 0; xb < nxm; ++xb)
+        for (int yb = 0; yb < nym; ++yb) {
+            if (msym && kTileN * yb + kTileN - 1 < kTileM * xb) continue;
+            tm.push_back({xb, yb});
+            cm.push_back(cm.back() + k2_tile_cost(xb, yb, (int)naux, (int)nq, msym, c.k2_mask));
+        }
+    { int r = grow(c.d_tm, c.tm_cap, tm.size(), false); if (r) return r; }
+    { int r = grow(c.d_cm, c.cm_cap, cm.size(), false); if (r) return r; }
+    CU_TRY(cudaMemcpyAsync(c.d_tm, tm.data(), tm.size() * sizeof(K2Tile), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c.d_cm, cm.data(), cm.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));   // tm / cm are pageable host memory
+    record(st, 2, true);
+    for (const Pass& ps : passes) {
+        const Spin& sp = *ps.sp;
+        const int nki = (int)((sp.nvir + kKB - 1) / kKB);
+        const int64_t kpad = (int64_t)nki * kKB;
+        for (int b = 0; b < 2; ++b) { int r = grow(c.wq[b], c.wq_elems[b], (size_t)(sp.nocc * kpad), false); if (r) return r; }
+        dim3 gw((unsigned)((kpad + 127) / 128), (unsigned)sp.nocc);
+        const bool is_same = ps.sp == &same;
+        fill_m_weights<<<gw, 128, 0, st>>>(c.wq[0], c.wq[1], sp.ei_dev, sp.ea_dev, (int)sp.nvir, (int)kpad, ps.w_in,
+                                          ps.w_out, is_same ? (int)istart : 0, is_same ? (int)iend : (int)sp.nocc);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+        K2Launch L;
+        cuuint64_t d[3] = {(cuuint64_t)sp.nvir, (cuuint64_t)sp.nocc, (cuuint64_t)naux};
+        cuuint64_t sb[2] = {(cuuint64_t)sp.ld * 8, (cuuint64_t)sp.ld * 8 * (cuuint64_t)sp.nocc};
+        cuuint32_t bx[3] = {kKB, 1, 64};
+        if (int r = make_map(&L.a0, sp.qja, 3, d, sb, bx)) return r;
+        L.a1 = L.a0; L.b = L.a0;
+        L.mode = 1;
+        L.total_cost = cm.back();
+        L.p = K2Params{c.wq[0], c.wq[1], c.d_tm, c.d_cm, c.Mbuf, c.Mbuf + nq_pad, ldm, (int)tm.size(), nki,
+                       (int)sp.nocc, 1, 1, 0, 0, (int)q_lo, (int)naux, (int)nq, msym, c.k2_mask};
+        if (int r = launch_k2(L, st)) return r;
+    }
+    if (msym) {
+        dim3 gm((unsigned)((naux + 127) / 128), (unsigned)naux);
+        mirror_m<<<gm, 128, 0, st>>>(c.Mbuf, (int)naux, nq_pad, ldm);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+    }
+    record(st, 2, false);
+
+    // ---- T = ixq_batch [M0 | M1], then the two moments ------------------------------------------------------
+    const int64_t per_pole = nphys * ldm;
+    const int64_t nbi_max = std::max<int64_t>(1, std::min<int64_t>(64, (512ll << 20) / (per_pole * 8)));
+    const int nkq = (int)((nq + kKB - 1) / kKB);
+    const int64_t kpad = (int64_t)nkq * kKB;
+    { int r = grow(c.Tbuf[0], c.t_elems[0], (size_t)(std::min<int64_t>(nbi_max, iend - istart) * per_pole), false); if (r) return r; }
+    { int r = grow(c.we[0], c.we_elems[0], (size_t)(nbi_max * kpad), false); if (r) return r; }
+    if (cublasSetStream(c.blas, st) != CUBLAS_STATUS_SUCCESS) return fail(AGF2_B200_ESOLVER, "cublasSetStream failed");
+    CUtensorMap mapIx;
+    {
+        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)same.nocc};
+        cuuint64_t sb[2] = {(cuuint64_t)ld_ixq * 8, (cuuint64_t)ld_ixq * 8 * (cuuint64_t)nphys};
+        cuuint32_t bx[3] = {kKB, 64, 1};
+        if (int r = make_map(&mapIx, ixq, 3, d, sb, bx)) return r;
+    }
+    record(st, 3, true);
+    for (int64_t i0 = istart; i0 < iend; i0 += nbi_max) {
+        const int64_t nbi = std::min<int64_t>(nbi_max, iend - i0);
+        const double one = 1.0, zero = 0.0;
+        // row-major T (nbi*P x ldm) = IXQ (nbi*P x naux) . M (naux x ldm)   ==   column-major T^T = M^T IXQ^T
+        cublasStatus_t bs = cublasDgemm(c.blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)ldm, (int)(nbi * nphys), (int)naux, &one,
+                                        c.Mbuf, (int)ldm, ixq + i0 * nphys * ld_ixq, (int)ld_ixq, &zero, c.Tbuf[0],
+                                        (int)ldm);
+        if (bs != CUBLAS_STATUS_SUCCESS) return fail(AGF2_B200_ESOLVER, "cublasDgemm (Coulomb T) failed with status " + std::to_string((int)bs));
+        c.launches++;
+        dim3 ge((unsigned)((kpad + 127) / 128), (unsigned)nbi);
+        fill_e_weights<<<ge, 128, 0, st>>>(c.we[0], same.ei_dev, (int)i0, (int)kpad);
+        CU_TRY(cudaGetLastError());
+        c.launches++;
+        K2Launch L;
+        cuuint64_t d[3] = {(cuuint64_t)nq, (cuuint64_t)nphys, (cuuint64_t)nbi};
+        cuuint64_t sb[2] = {(cuuint64_t)ldm * 8, (cuuint64_t)ldm * 8 * (cuuint64_t)nphys};
+        cuuint32_t bx[3] = {kKB, 64, 1};
+        if (int r = make_map(&L.a0, c.Tbuf[0], 3, d, sb, bx)) return r;
+        if (int r = make_map(&L.a1, c.Tbuf[0] + nq_pad, 3, d, sb, bx)) return r;
+        L.b = mapIx;
+        L.mode = 2;
+        L.total_cost = cost_sym;
+        L.p = K2Params{nullptr, c.we[0], d_t2_sym, d_cost_sym, S_vv, S_vev, p_pad, nt_sym, nkq, (int)nbi, 0, 0,
+                       (int)q_lo, (int)i0, 0, (int)nphys, (int)nphys, 1, c.k2_mask};
+        if (int r = launch_k2(L, st)) return r;
+    }
+    record(st, 3, false);
+    return 0;
+}
+
 // The whole moment build on device-resident inputs.
 int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other,
                 const double* ei_same_host, const double* ei_other_host, int64_t nphys, int64_t naux,
@@ -260,15 +423,39 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     if ((reinterpret_cast<uintptr_t>(ixq) & 15) || (reinterpret_cast<uintptr_t>(same.qja) & 15) ||
         (other && (reinterpret_cast<uintptr_t>(other->qja) & 15)))
         return fail(AGF2_B200_EINVAL, "device arrays must be 16-byte aligned");
-    if (nphys > (1 << 30) || naux > (1 << 30) || o * v > (1ll << 40)) return fail(AGF2_B200_EINVAL, "dimension too large");
+    if (nphys > (1 << 30) || naux > (1 << 30) || o * v > (1ll << 40) || o > 65535 || (other && other->nocc > 65535))
+        return fail(AGF2_B200_EINVAL, "dimension too large");
 
     const int64_t p_pad = rup(nphys, kTileM);
     const int nxb = (int)(p_pad / kTileM);
     const int nyb = (int)((nphys + kTileN - 1) / kTileN);
     const int64_t vpad = rup(v, 8);
     const int64_t vbpad = other ? rup(other->nvir, 8) : 0;
-    const double ca = std::sqrt(0.5 * (c_same + s_same)), cs = std::sqrt(0.5 * (c_same - s_same));
-    const double cd = std::sqrt(c_same - s_same), co = std::sqrt(os_other);
+    // Coulomb factorisation (default): the pair loop only carries the exchange-type term  s sum_{i>j} A A^T,
+    // A = X_ij - X_ji; every Coulomb-type term goes through run_coulomb.  Otherwise (debug / simple kernels):
+    // pairs carry sqrt(c/2+s/2) A and sqrt(c/2-s/2) S, plus DIAG and OS items.
+    bool fact = c.coulomb && !c.simple;
+    if (fact && c.coulomb_auto) {
+        // flops the factorisation removes from the pair loop (S blocks, DIAG and OS items) vs the flops it adds
+        const double P = (double)nphys, N = (double)naux, ni = (double)(iend - istart), tri = 0.61;
+        const double no = (double)o, ov = no * (double)v;
+        const double obvb = other ? (double)other->nocc * (double)other->nvir : 0.0;
+        const double k2col = 2.0 * tri * 2.0 * P * P;                       // both moments, per workspace column
+        double direct = 0.5 * ni * (ni - 1.0) * v * k2col * (c_same != s_same ? 1.0 : 0.0);   // S blocks
+        direct += (c_same != s_same ? ni * ((double)v * k2col + 2.0 * P * v * N) : 0.0);         // DIAG items
+        direct += os_other != 0.0 ? ni * (obvb * k2col + 2.0 * P * obvb * N) : 0.0;             // OS items
+        const bool partial_slice = istart > 0 || iend < o;
+        double mcols = 0.0;                                                  // (j, a) columns of the M build
+        if (c_same != s_same || (partial_slice && c_same != 0.0)) mcols += ov;
+        if (os_other != 0.0) mcols += obvb;
+        const double fwork = (nparts == 1 ? 0.5 : 1.0) * 4.0 * N * N * mcols + ni * (4.0 * P * N * N + k2col * N);
+        fact = mcols > 0.0 && fwork < 0.95 * direct;
+    }
+    const double ca = fact ? std::sqrt(s_same) : std::sqrt(0.5 * (c_same + s_same));
+    const double cs = fact ? 0.0 : std::sqrt(0.5 * (c_same - s_same));
+    const double cd = fact ? 0.0 : std::sqrt(c_same - s_same), co = fact ? 0.0 : std::sqrt(os_other);
+    const double asym_c = fact ? 0.0 : c_same;
+    const bool want_asym = !(fact && s_same == 0.0);
 
     // ---- scratch ------------------------------------------------------------------------------
     int64_t cap_cols = std::max<int64_t>(c.ws_bytes / (p_pad * 8), 2 * std::max(vpad, vbpad));
@@ -336,13 +523,15 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
         std::vector<Item> diag_items, os_items;
         for (int64_t i = istart; i < iend; ++i) {
             if (cd != 0.0 && (n_diag++ % nparts) == part) diag_items.push_back({0, (int)i, (int)i});
-            for (int64_t j = istart; j < i; ++j)
-                if ((n_pair++ % nparts) == part) sym_items.push_back({1, (int)i, (int)j});
+            if (ca != 0.0 || cs != 0.0)
+                for (int64_t j = istart; j < i; ++j)
+                    if ((n_pair++ % nparts) == part) sym_items.push_back({1, (int)i, (int)j});
             if (other && co != 0.0)
                 for (int64_t J = 0; J < other->nocc; ++J)
                     if ((n_os++ % nparts) == part) os_items.push_back({2, (int)i, (int)J});
-            for (int64_t j = 0; j < o; ++j)
-                if ((j < istart || j >= iend) && (n_asym++ % nparts) == part) asym_items.push_back({3, (int)i, (int)j});
+            if (want_asym)
+                for (int64_t j = 0; j < o; ++j)
+                    if ((j < istart || j >= iend) && (n_asym++ % nparts) == part) asym_items.push_back({3, (int)i, (int)j});
         }
         sym_items.insert(sym_items.end(), diag_items.begin(), diag_items.end());
         sym_items.insert(sym_items.end(), os_items.begin(), os_items.end());
@@ -386,10 +575,17 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             t2_all.push_back({xb, yb});
             if (kTileN * yb + kTileN - 1 >= kTileM * xb) t2_sym.push_back({xb, yb});
         }
+    // stream-K cost prefixes: edge tiles (diagonal, padded last row / column) skip the DMMAs they do not need
+    std::vector<int> cost_sym(1, 0), cost_all(1, 0);
+    for (const K2Tile& t : t2_sym) cost_sym.push_back(cost_sym.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 1, c.k2_mask));
+    for (const K2Tile& t : t2_all) cost_all.push_back(cost_all.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 0, c.k2_mask));
     { int r = grow(c.d_t2, c.t2_cap, t2_sym.size() + t2_all.size(), false); if (r) return r; }
+    { int r = grow(c.d_cost, c.cost_cap, cost_sym.size() + cost_all.size(), false); if (r) return r; }
     CU_TRY(cudaMemcpyAsync(c.d_t2, t2_sym.data(), t2_sym.size() * sizeof(K2Tile), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(c.d_t2 + t2_sym.size(), t2_all.data(), t2_all.size() * sizeof(K2Tile), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));   // t2 vectors are pageable host memory
+    CU_TRY(cudaMemcpyAsync(c.d_cost, cost_sym.data(), cost_sym.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c.d_cost + cost_sym.size(), cost_all.data(), cost_all.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));   // these vectors are pageable host memory
 
     c.events_used = 0;
     int64_t& chunk_idx = c.chunk_counter;   // global: tile staging buffers alternate across calls too
@@ -435,8 +631,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                                 t.ws2 = cs != 0.0 ? 0 : -1; t.p21 = cs; t.p22 = cs;
                             } else {
                                 t.ws1 = 0; t.p11 = 1.0; t.p12 = 0.0;
-                                t.ws2 = 1; t.p21 = c_same; t.p22 = -s_same;
-                                if (t.p21 == 0.0) t.p21 = 0.0;   // (c = 0: out2 width falls back to nb2 == nb1)
+                                t.ws2 = 1; t.p21 = asym_c; t.p22 = -s_same;   // (p21 = 0: out2 width falls back to nb2 == nb1)
                             }
                             tiles.push_back(t);
                         }
@@ -541,26 +736,28 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             const std::vector<K2Tile>& t2 = sym ? t2_sym : t2_all;
             const K2Tile* d_t2 = sym ? c.d_t2 : c.d_t2 + t2_sym.size();
             const int nk2 = (int)((col + kKB - 1) / kKB);
-            // stream-K grid: one CTA per SM, unless the chunk is too small to give each >= 8 iterations
-            const long long total_it = (long long)t2.size() * nk2;
-            const int grid2 = (int)std::max<long long>(1, std::min<long long>(c.num_sms, total_it / 8));
             record(sc, 1, true);
             if (!c.simple) {
-                CUtensorMap mapWA, mapWB;
-                cuuint64_t d[2] = {(cuuint64_t)col, (cuuint64_t)p_pad};
-                cuuint64_t s[1] = {(cuuint64_t)ldw * 8};
-                cuuint32_t b[2] = {kKB, 64};
-                if (int r = make_map(&mapWA, Wa, 2, d, s, b)) return r;
-                if (int r = make_map(&mapWB, sym ? Wa : Wb, 2, d, s, b)) return r;
-                k2_moment<<<grid2, kThreads, kK2SmemBytes, sc>>>(mapWA, mapWB, Ebuf, d_t2, sym ? S_vv : A_vv,
-                                                                sym ? S_vev : A_vev, p_pad, nk2, (int)t2.size());
+                K2Launch L;
+                cuuint64_t d[3] = {(cuuint64_t)col, (cuuint64_t)p_pad, 1};
+                cuuint64_t s[2] = {(cuuint64_t)ldw * 8, (cuuint64_t)ldw * 8 * (cuuint64_t)p_pad};
+                cuuint32_t b[3] = {kKB, 64, 1};
+                if (int r = make_map(&L.a0, Wa, 3, d, s, b)) return r;
+                if (int r = make_map(&L.b, sym ? Wa : Wb, 3, d, s, b)) return r;
+                L.a1 = L.a0;
+                L.mode = 0;
+                L.total_cost = sym ? cost_sym.back() : cost_all.back();
+                L.p = K2Params{nullptr, Ebuf, d_t2, sym ? c.d_cost : c.d_cost + cost_sym.size(), sym ? S_vv : A_vv,
+                               sym ? S_vev : A_vev, p_pad, (int)t2.size(), nk2, 1, 0, 0, 0, 0, 0, (int)nphys, (int)nphys,
+                               sym ? 1 : 0, c.k2_mask};
+                if (int r = launch_k2(L, sc)) return r;
             } else {
                 k2_moment_simple<<<(unsigned)t2.size(), 256, 0, sc>>>(Wa, sym ? Wa : Wb, ldw, Ebuf, (int)col,
                                                                       d_t2, sym ? S_vv : A_vv, sym ? S_vev : A_vev, p_pad);
+                CU_TRY(cudaGetLastError());
+                c.launches++;
             }
             record(sc, 1, false);
-            CU_TRY(cudaGetLastError());
-            c.launches++;
             ++chunk_idx;
         }
         return 0;
@@ -568,6 +765,20 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
 
     if (int r = run_chunks(sym_items, true)) return r;
     if (int r = run_chunks(asym_items, false)) return r;
+    if (fact) {
+        if (gate) {   // host-pointer API: every pole of the slice must have landed
+            const int need = (int)(iend - istart) - 1;
+            while (gate->ready->load(std::memory_order_acquire) <= need) {
+                if (gate->failed->load()) return fail(AGF2_B200_ECUDA, "ixq upload failed");
+                std::this_thread::yield();
+            }
+            CU_TRY(cudaStreamWaitEvent(st, (*gate->ev)[need], 0));
+        }
+        // weights of the Coulomb-type terms: same-spin tensor (c - s) [+ s for j outside the slice], other spin os
+        if (int r = run_coulomb(ixq, ld_ixq, same, other, nphys, naux, istart, iend, c_same - s_same, c_same, os_other,
+                                part, nparts, S_vv, S_vev, p_pad, c.d_t2, c.d_cost, (int)t2_sym.size(), cost_sym.back(), st))
+            return r;
+    }
 
     if (used2) {
         CU_TRY(cudaEventRecord(c.ev_k2[0], c.stream2));
@@ -584,7 +795,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
 int finish_profile(cudaStream_t st) {
     Ctx& c = g_ctx;
     CU_TRY(cudaStreamSynchronize(st));
-    c.last_ms[0] = c.last_ms[1] = 0;
+    for (int k = 0; k < 4; ++k) c.last_ms[k] = 0;
     for (size_t k = 0; k < c.events_used; ++k) {
         float ms = 0;
         cudaEventElapsedTime(&ms, c.events[k].a, c.events[k].b);
@@ -685,6 +896,19 @@ int64_t agf2_b200_launch_count(int reset) {
     return n;
 }
 
+int agf2_b200_last_stage_ms(double* ms4) {
+    if (!ms4) return fail(AGF2_B200_EINVAL, "null pointer");
+    for (int k = 0; k < 4; ++k) ms4[k] = g_ctx.last_ms[k];
+    return 0;
+}
+
+int agf2_b200_set_coulomb_factorization(int mode) {
+    if (mode < 0 || mode > 2) return fail(AGF2_B200_EINVAL, "mode must be 0 (off), 1 (always) or 2 (automatic)");
+    g_ctx.coulomb = mode != 0;
+    g_ctx.coulomb_auto = mode == 2;
+    return 0;
+}
+
 int agf2_b200_last_kernel_ms(double* k1, double* k2) {
     if (k1) *k1 = g_ctx.last_ms[0];
     if (k2) *k2 = g_ctx.last_ms[1];
@@ -704,7 +928,7 @@ static int moments_rhf_impl(const double* ixq, int64_t ld_ixq, const double* qja
     CU_TRY(cudaMemcpyAsync(ei_h.data(), ei, nocc * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     Spin same;
-    same.qja = qja; same.ld = ld_qja; same.nocc = nocc; same.nvir = nvir; same.ea_dev = ea;
+    same.qja = qja; same.ld = ld_qja; same.nocc = nocc; same.nvir = nvir; same.ea_dev = ea; same.ei_dev = ei;
     int r = run_moments(ixq, ld_ixq, same, nullptr, ei_h.data(), nullptr, nphys, naux, istart, iend,
                         os_factor + ss_factor, ss_factor, 0.0, part, nparts, vv, vev, st, gate);
     if (r) return r;
@@ -739,8 +963,8 @@ static int moments_uhf_impl(const double* ixq_a, int64_t ld_ixq, const double* q
     if (has_b) CU_TRY(cudaMemcpyAsync(eib.data(), ei_b, nocc_b * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     Spin same, other;
-    same.qja = qja_a; same.ld = ld_qja_a; same.nocc = nocc_a; same.nvir = nvir_a; same.ea_dev = ea_a;
-    other.qja = qja_b; other.ld = ld_qja_b; other.nocc = nocc_b; other.nvir = nvir_b; other.ea_dev = ea_b;
+    same.qja = qja_a; same.ld = ld_qja_a; same.nocc = nocc_a; same.nvir = nvir_a; same.ea_dev = ea_a; same.ei_dev = ei_a;
+    other.qja = qja_b; other.ld = ld_qja_b; other.nocc = nocc_b; other.nvir = nvir_b; other.ea_dev = ea_b; other.ei_dev = ei_b;
     // same-spin: Coulomb ss, exchange ss (optuagf2.c:211-256); opposite spin: Coulomb os
     int r = run_moments(ixq_a, ld_ixq, same, has_b ? &other : nullptr, eia.data(), eib.data(), nphys, naux, istart,
                         iend, ss_factor, ss_factor, os_factor, part, nparts, vv, vev, st, gate);

@@ -17,6 +17,7 @@
 //   k3_finalize : mirrors the upper triangle, adds the non-symmetric part, accumulates into vv/vev.
 //   *_simple    : naive one-thread-per-element versions of k1/k2 driven by the same tile lists (debug).
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace agf2 {
@@ -274,37 +275,118 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------
+// One kernel, three uses (all: acc_vv += A' B^T, acc_vev += A'' B^T on 128 x 64 output tiles, K streamed through a
+// TMA/mbarrier ring, stream-K over the SMs):
+//   moments   <false,false>  A = B = W (workspace chunk), A'' = A diag(w1), w1 = E          (optragf2.c:206-290)
+//   M build   <false,true >  A = B = (Q|ja) with rows Q and K = (j, a): A' = A diag(w0), A'' = A diag(w1);
+//                            M0 = sum_ja w0 q q^T, M1 = sum_ja w0 (e_j - e_a) q q^T           (Coulomb factorisation)
+//   Coulomb   <true ,false>  A = T0 = ixq_i M0, A1 = T1 = ixq_i M1, B = ixq_i, K = (i, Q):
+//                            vv += T0 B^T, vev += (e_i T0 + T1) B^T, w1 = e_i
+// Operands are 3-D tensor maps (k, row, outer) -- or (k, outer, row) when swap is set -- with 16 x 64 x 1 boxes;
+// the K iteration `kit` addresses outer = kit / nk_inner, k = 16 (kit % nk_inner); weights are indexed 16 kit + k.
 struct K2Tile {
     int xb, yb;   // rows [128*xb, +128) of operand A, rows [64*yb, +64) of operand B
 };
 
-constexpr int kK2StageBytes = kTileM * kKB * 8 + kTileN * kKB * 8 + 1024;  // A 16K + B 8K + E(128B, padded)
-constexpr int kK2Stages = 7;
-constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 256;
+struct K2Params {
+    const double* w0;        // per-column weights of the vv operand (kW0 only)
+    const double* w1;        // per-column weights of the vev operand
+    const K2Tile* tiles;
+    const int* cost_prefix;  // [ntiles + 1] cumulative tile cost (sixteenths of a full tile)
+    double* acc_vv;
+    double* acc_vev;
+    long long ldacc;
+    int ntiles, nk_inner, n_outer;
+    int swap_a, swap_b;      // operand maps are (k, outer, row) instead of (k, row, outer)
+    int b_k_off, b_outer_off, b_row_off;
+    int rows_valid, cols_valid;   // logical extent of the output (masks out padded warps / column blocks)
+    int sym;                 // only the blocks touching the upper triangle are computed
+    int mask;                // 0: every warp computes all 8 column blocks of every tile; 1: warps with nothing
+                             // to do on an edge tile skip it; 2: partially needed warps also skip column blocks
+                             // (predicated DMMAs -- measured slower than computing the padding)
+};
 
-__global__ void __launch_bounds__(kThreads, 1)
-k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUtensorMap mapWB,
-          const double* __restrict__ E, const K2Tile* __restrict__ tiles,
-          double* __restrict__ acc_vv, double* __restrict__ acc_vev, long long ldacc,
-          int nk_total, int ntiles)
+constexpr int kK2StageBytes = kTileM * kKB * 8 + kTileN * kKB * 8 + 1024;  // A 16K + B 8K + weights (2 x 128 B, padded)
+constexpr int kK2StageBytesDual = kK2StageBytes + kTileM * kKB * 8;        // + A1 16K
+constexpr int kK2Stages = 7, kK2StagesDual = 5;
+constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 256;
+constexpr int kK2SmemBytesDual = kK2StagesDual * kK2StageBytesDual + 1024 + 256;
+
+// Column blocks [lo, hi) of a tile that warp `warp` (rows 16 warp .. +15 of the tile) has to compute.
+__host__ __device__ inline void k2_warp_range(int xb, int yb, int warp, int rows_valid, int cols_valid, int sym,
+                                              int mask, int& lo, int& hi)
 {
+    if (!mask) { lo = 0; hi = 8; return; }
+    const int row0 = xb * kTileM + 16 * warp, col0 = yb * kTileN;
+    hi = (cols_valid - col0 + 7) / 8;
+    hi = hi < 0 ? 0 : (hi > 8 ? 8 : hi);
+    lo = 0;
+    if (row0 >= rows_valid) hi = 0;
+    if (sym && row0 > col0) lo = (row0 - col0) / 8;   // blocks entirely below the diagonal are skipped
+    if (lo >= hi) lo = hi = 0;
+    else if (mask < 2) { lo = 0; hi = 8; }
+}
+// Cost of a tile in sixteenths of a full one: the busiest SM sub-partition (warps w and w + 4 share one).
+// A partially masked warp still issues its predicated-off DMMAs, so it never costs less than half a full one;
+// a fully masked warp branches over the unit.
+__host__ __device__ inline int k2_tile_cost(int xb, int yb, int rows_valid, int cols_valid, int sym, int mask)
+{
+    int worst = 0;
+    for (int s = 0; s < 4; ++s) {
+        int sum = 0;
+        for (int w = s; w < 8; w += 4) {
+            int lo, hi;
+            k2_warp_range(xb, yb, w, rows_valid, cols_valid, sym, mask, lo, hi);
+            const int n = hi - lo;
+            sum += n == 0 ? 0 : (n < 4 ? 4 : n);
+        }
+        worst = sum > worst ? sum : worst;
+    }
+    return worst < 4 ? 4 : worst;   // shared-memory traffic and barriers do not shrink with the mask
+}
+
+// stream-K boundary b of G: position (tile, kit) at cost  total * b / G
+__device__ __forceinline__ void k2_boundary(const int* __restrict__ prefix, int ntiles, int nk, int b, int G,
+                                            int& tile, int& kit)
+{
+    const long long total = (long long)prefix[ntiles] * nk;
+    const long long u = total * b / G;
+    int lo = 0, hi = ntiles;   // largest t with prefix[t] * nk <= u
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((long long)prefix[mid] * nk <= u) lo = mid; else hi = mid - 1;
+    }
+    tile = lo;
+    kit = 0;
+    if (tile < ntiles) kit = (int)((u - (long long)prefix[tile] * nk) / (prefix[tile + 1] - prefix[tile]));
+}
+
+template <bool kDual, bool kW0>
+__global__ void __launch_bounds__(kThreads, 1)
+k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapB, const __grid_constant__ K2Params p)
+{
+    constexpr int kStages = kDual ? kK2StagesDual : kK2Stages;
+    constexpr int kStageBytes = kDual ? kK2StageBytesDual : kK2StageBytes;
+    constexpr uint32_t kOffB = 16384, kOffW = 24576, kOffA1 = 25600;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_full = base + kK2Stages * kK2StageBytes;
-    const uint32_t bar_empty = bar_full + 8 * kK2Stages;
+    const uint32_t bar_full = base + kStages * kStageBytes;
+    const uint32_t bar_empty = bar_full + 8 * kStages;
     uint8_t* const gbase = smem_raw + (base - smem_u32(smem_raw));
 
-    // stream-K: the (tile, k-iteration) space is linearised tile-major and cut into gridDim.x equal
-    // ranges, so every SM gets the same number of DMMA iterations whatever the tile count; a CTA
-    // flushes its accumulators (red.global.add) whenever its range crosses a tile boundary.
-    const long long total = (long long)ntiles * nk_total;
-    const long long L0 = total * blockIdx.x / gridDim.x;
-    const long long L1 = total * (blockIdx.x + 1) / gridDim.x;
-    const int nk = (int)(L1 - L0);
+    // stream-K: the (tile, k-iteration) space, weighted by tile cost, is cut into gridDim.x equal ranges so
+    // that every SM gets the same amount of DMMA work whatever the tile count; a CTA flushes its accumulators
+    // (red.global.add) whenever its range crosses a tile boundary.
+    const int nk_total = p.nk_inner * p.n_outer;
+    int tile, kit, tile_end, kit_end;
+    k2_boundary(p.cost_prefix, p.ntiles, nk_total, blockIdx.x, gridDim.x, tile, kit);
+    k2_boundary(p.cost_prefix, p.ntiles, nk_total, blockIdx.x + 1, gridDim.x, tile_end, kit_end);
+    const int nk = (tile_end - tile) * nk_total + kit_end - kit;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kK2Stages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, kConsumerWarps);
         }
@@ -317,23 +399,41 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
     if (warp >= kConsumerWarps) {
         reg_dealloc_producer();
         if (warp == kConsumerWarps && lane == 0) {
-            tma_prefetch_desc(&mapWA);
-            tma_prefetch_desc(&mapWB);
-            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8;
-            int tile = (int)(L0 / nk_total), kit = (int)(L0 % nk_total);
-            K2Tile t = tiles[tile];
+            tma_prefetch_desc(&mapA0);
+            tma_prefetch_desc(&mapB);
+            if (kDual) tma_prefetch_desc(&mapA1);
+            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8 + (kW0 ? kKB * 8 : 0) +
+                                       (kDual ? kTileM * kKB * 8 : 0);
+            K2Tile t = p.tiles[tile];
+            int outer = kit / p.nk_inner, ki = kit % p.nk_inner;
             for (int j = 0; j < nk; ++j) {
-                const int s = j % kK2Stages;
-                if (j >= kK2Stages) mbar_wait(bar_empty + 8 * s, ((j / kK2Stages) - 1) & 1);
-                const uint32_t st = base + s * kK2StageBytes;
+                const int s = j % kStages;
+                if (j >= kStages) mbar_wait(bar_empty + 8 * s, ((j / kStages) - 1) & 1);
+                const uint32_t st = base + s * kStageBytes;
                 const uint32_t fb = bar_full + 8 * s;
                 mbar_expect_tx(fb, bytes);
-                const int k0 = kit * kKB;
-                tma_load_2d(st, &mapWA, k0, t.xb * kTileM, fb);
-                tma_load_2d(st + 8192, &mapWA, k0, t.xb * kTileM + 64, fb);
-                tma_load_2d(st + 16384, &mapWB, k0, t.yb * kTileN, fb);
-                bulk_load_1d(st + 24576, E + k0, kKB * 8, fb);
-                if (++kit == nk_total && j + 1 < nk) { kit = 0; t = tiles[++tile]; }
+                const int k0 = ki * kKB;
+                const int ra = t.xb * kTileM, rb = t.yb * kTileN + p.b_row_off, ob = outer + p.b_outer_off;
+                if (p.swap_a) {
+                    tma_load_3d(st, &mapA0, k0, outer, ra, fb);
+                    tma_load_3d(st + 8192, &mapA0, k0, outer, ra + 64, fb);
+                } else {
+                    tma_load_3d(st, &mapA0, k0, ra, outer, fb);
+                    tma_load_3d(st + 8192, &mapA0, k0, ra + 64, outer, fb);
+                }
+                if (kDual) {
+                    tma_load_3d(st + kOffA1, &mapA1, k0, ra, outer, fb);
+                    tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, ra + 64, outer, fb);
+                }
+                if (p.swap_b) tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, ob, rb, fb);
+                else tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, rb, ob, fb);
+                const long long wi = ((long long)outer * p.nk_inner + ki) * kKB;
+                bulk_load_1d(st + kOffW, p.w1 + wi, kKB * 8, fb);
+                if (kW0) bulk_load_1d(st + kOffW + 128, p.w0 + wi, kKB * 8, fb);
+                if (++ki == p.nk_inner) {
+                    ki = 0;
+                    if (++outer == p.n_outer) { outer = 0; if (j + 1 < nk) t = p.tiles[++tile]; }
+                }
             }
         }
         return;
@@ -356,22 +456,32 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
         }
 
     // One stage = 4 units (ks, half): unit u+1's fragments are loaded while unit u's 32 DMMAs issue.
-    double2 fa[2][2], fe[2][2];   // [ks parity][mb]: A fragments and their energy-weighted copies
+    double2 fa[2][2], fe[2][2];   // [ks parity][mb]: fragments of the vv operand and of the vev operand
     double2 fb[2][4];             // [half][j]: B fragments of n-blocks 4*half + j
     auto load_unit = [&](const uint8_t* st, int u) {
         const int ks = u >> 1, half = u & 1;
         if (half == 0) {
-            const double2 ev = *reinterpret_cast<const double2*>(st + 24576 + (4 * ks + tig) * 16);
+            const double2 ev = *reinterpret_cast<const double2*>(st + kOffW + (4 * ks + tig) * 16);
+            double2 ev0;
+            if (kW0) ev0 = *reinterpret_cast<const double2*>(st + kOffW + 128 + (4 * ks + tig) * 16);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
-                fa[ks][mb] = *reinterpret_cast<const double2*>(st + a_row + mb * 1024 + sw[ks]);
-                fe[ks][mb].x = fa[ks][mb].x * ev.x;
-                fe[ks][mb].y = fa[ks][mb].y * ev.y;
+                double2 a = *reinterpret_cast<const double2*>(st + a_row + mb * 1024 + sw[ks]);
+                if (kDual) {
+                    const double2 a1 = *reinterpret_cast<const double2*>(st + kOffA1 + a_row + mb * 1024 + sw[ks]);
+                    fe[ks][mb].x = fma(a.x, ev.x, a1.x);
+                    fe[ks][mb].y = fma(a.y, ev.y, a1.y);
+                } else {
+                    fe[ks][mb].x = a.x * ev.x;
+                    fe[ks][mb].y = a.y * ev.y;
+                }
+                if (kW0) { a.x *= ev0.x; a.y *= ev0.y; }
+                fa[ks][mb] = a;
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-            fb[half][j] = *reinterpret_cast<const double2*>(st + 16384 + b_row + (4 * half + j) * 1024 + sw[ks]);
+            fb[half][j] = *reinterpret_cast<const double2*>(st + kOffB + b_row + (4 * half + j) * 1024 + sw[ks]);
     };
     auto compute_unit = [&](int u) {
         const int ks = u >> 1, half = u & 1;
@@ -390,49 +500,116 @@ k2_moment(const __grid_constant__ CUtensorMap mapWA, const __grid_constant__ CUt
             }
         }
     };
+    // edge tiles (diagonal, padded last row / column): only the column blocks [lo, hi) of this warp
+    auto compute_unit_masked = [&](int u, int lo, int hi) {
+        const int ks = u >> 1, half = u & 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nb = 4 * half + j;
+            if (nb >= lo && nb < hi) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].x, fb[half][j].x);
+                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].x, fb[half][j].x);
+                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].y, fb[half][j].y);
+                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].y, fb[half][j].y);
+                }
+            }
+        }
+    };
 
-    int tile = (int)(L0 / nk_total), kit = (int)(L0 % nk_total);
+    K2Tile t = p.tiles[tile];
+    int lo, hi;
+    k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, p.mask, lo, hi);
     mbar_wait(bar_full, 0);
     load_unit(gbase, 0);
-    for (int it = 0; it < nk; ++it) {
-        const int s = it % kK2Stages;
-        const uint8_t* st = gbase + s * kK2StageBytes;
+    // One iteration = one pipeline stage.  kMode 0: all 8 column blocks (the hot loop), 1: blocks [lo, hi),
+    // 2: nothing to compute for this warp (it only keeps the pipeline moving).
+    auto iteration = [&](int it, auto mode) {
+        constexpr int kMode = decltype(mode)::value;
+        const int s = it % kStages;
+        const uint8_t* st = gbase + s * kStageBytes;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (u < 3) {
-                load_unit(st, u + 1);
-            } else if (it + 1 < nk) {
-                const int s2 = (it + 1) % kK2Stages;
-                mbar_wait(bar_full + 8 * s2, ((it + 1) / kK2Stages) & 1);
-                load_unit(gbase + s2 * kK2StageBytes, 0);
+            if (kMode != 2) {
+                if (u < 3) {
+                    load_unit(st, u + 1);
+                } else if (it + 1 < nk) {
+                    const int s2 = (it + 1) % kStages;
+                    mbar_wait(bar_full + 8 * s2, ((it + 1) / kStages) & 1);
+                    load_unit(gbase + s2 * kStageBytes, 0);
+                }
+                if (kMode == 0) compute_unit(u);
+                else compute_unit_masked(u, lo, hi);
             }
-            compute_unit(u);
+        }
+        if (kMode == 2 && it + 1 < nk) {
+            const int s2 = (it + 1) % kStages;
+            mbar_wait(bar_full + 8 * s2, ((it + 1) / kStages) & 1);
+            load_unit(gbase + s2 * kStageBytes, 0);   // the next tile may need this warp again
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-        if (++kit == nk_total || it + 1 == nk) {
-            // split-K / cross-chunk reduction: warp-level fragments straight into the global accumulators
-            const K2Tile t = tiles[tile];
-            const long long x0 = (long long)t.xb * kTileM + 16 * warp;
-            const long long y0 = (long long)t.yb * kTileN;
+    };
+    int it = 0;
+    while (it < nk) {
+        const int seg_end = min(nk, it + nk_total - kit);   // this tile's share of the range
+        if (lo == 0 && hi == 8) { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 0>()); }
+        else if (hi > lo) { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 1>()); }
+        else { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 2>()); }
+        // split-K / cross-chunk reduction: warp-level fragments straight into the global accumulators
+        const long long x0 = (long long)t.xb * kTileM + 16 * warp;
+        const long long y0 = (long long)t.yb * kTileN;
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                const long long row = x0 + 8 * mb + pg;
+        for (int mb = 0; mb < 2; ++mb) {
+            const long long row = x0 + 8 * mb + pg;
 #pragma unroll
-                for (int nb = 0; nb < 8; ++nb)
+            for (int nb = 0; nb < 8; ++nb)
+                if (nb >= lo && nb < hi) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const long long col = y0 + 8 * nb + pi8(2 * tig + h);
-                        red_add_f64(acc_vv + row * ldacc + col, cvv[mb][nb][h]);
-                        red_add_f64(acc_vev + row * ldacc + col, cvev[mb][nb][h]);
+                        red_add_f64(p.acc_vv + row * p.ldacc + col, cvv[mb][nb][h]);
+                        red_add_f64(p.acc_vev + row * p.ldacc + col, cvev[mb][nb][h]);
                         cvv[mb][nb][h] = 0.0;
                         cvev[mb][nb][h] = 0.0;
                     }
-            }
-            kit = 0;
-            ++tile;
+                }
+        }
+        kit = 0;
+        if (it < nk) {
+            t = p.tiles[++tile];
+            k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, p.mask, lo, hi);
         }
     }
+}
+
+// ---- per-column weights of the Coulomb factorisation ---------------------------------------------
+// M build: w0[j, a] = w_in (j in [istart, iend)) or w_out, 0 in the K padding; w1 = w0 (e_j - e_a)
+__global__ void fill_m_weights(double* __restrict__ w0, double* __restrict__ w1, const double* __restrict__ ej,
+                               const double* __restrict__ ea, int v, int kpad, double w_in, double w_out,
+                               int istart, int iend)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (a >= kpad) return;
+    const double w = (a < v) ? ((j >= istart && j < iend) ? w_in : w_out) : 0.0;
+    w0[(long long)j * kpad + a] = w;
+    w1[(long long)j * kpad + a] = (a < v) ? w * (ej[j] - ea[a]) : 0.0;
+}
+// M = [M0 | M1] (n rows, two n_pad-wide halves, pitch ld) was accumulated on its upper triangle: fill the lower one
+__global__ void mirror_m(double* __restrict__ m, int n, long long n_pad, long long ld)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c < r && c < n) {
+        m[(long long)r * ld + c] = m[(long long)c * ld + r];
+        m[(long long)r * ld + n_pad + c] = m[(long long)c * ld + n_pad + r];
+    }
+}
+// Coulomb step: we[il, k] = e_{i0 + il}
+__global__ void fill_e_weights(double* __restrict__ we, const double* __restrict__ ei, int i0, int kpad)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, il = blockIdx.y;
+    if (k < kpad) we[(long long)il * kpad + k] = ei[i0 + il];
 }
 
 // ---- K3: finalize ------------------------------------------------------------------------------

@@ -31,7 +31,8 @@ SYMBOLS = [
     "agf2_b200_set_device", "agf2_b200_set_workspace_bytes", "agf2_b200_build_part_loop_rhf",
     "agf2_b200_build_part_loop_uhf", "agf2_b200_moments_rhf_dev", "agf2_b200_moments_uhf_dev",
     "agf2_b200_compress", "agf2_b200_eigh", "agf2_b200_launch_count", "agf2_b200_last_kernel_ms",
-    "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap",
+    "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap", "agf2_b200_last_stage_ms",
+    "agf2_b200_set_coulomb_factorization",
 ]
 
 
@@ -100,6 +101,18 @@ def last_kernel_ms():
 
 def set_simple_kernels(on):
     check(_libagf2.agf2_b200_set_simple_kernels(1 if on else 0))
+
+
+def last_stage_ms():
+    """Device ms of the last synchronous moments call: (k1_form, k2_moment pairs, M build, Coulomb step)."""
+    out = (_dbl * 4)()
+    check(_libagf2.agf2_b200_last_stage_ms(out))
+    return tuple(out)
+
+
+def set_coulomb_factorization(mode):
+    """0 / False: off, 1 / True: always, 2: automatic (default)."""
+    check(_libagf2.agf2_b200_set_coulomb_factorization(int(mode)))
 
 
 def set_overlap(on):

@@ -156,6 +156,18 @@ int agf2_b200_get_jk(agf2_b200_eri *h, const double *rdm1, double *j, double *k,
 int64_t agf2_b200_launch_count(int reset);
 int agf2_b200_last_kernel_ms(double *k1_form_ms, double *k2_moment_ms);
 
+/* Device time (ms) of the last moments call by stage: [0] k1_form, [1] k2_moment of the pair loop, [2] the
+ * M0/M1 build and [3] the T = ixq M DGEMMs + moment accumulation of the Coulomb factorisation. */
+int agf2_b200_last_stage_ms(double *ms4);
+
+/* Coulomb factorisation (default on): every Coulomb-type term  sum_ija w X_ija X_ija^T (e_i+e_j-e_a)^n  of
+ * auxgf/lib/libagf2/optragf2.c:206-290 / optuagf2.c:211-314 is evaluated as  sum_i ixq_i (e_i^n M0 + n M1) ixq_i^T
+ * with the naux x naux matrices M0 = sum_ja w q_ja q_ja^T, M1 = sum_ja w (e_j - e_a) q_ja q_ja^T, so that only the
+ * exchange-type term  ss sum_{i>j} (X_ij - X_ji)(X_ij - X_ji)^T  goes through the pair loop.  Same result to
+ * rounding.  mode 0: off, every term goes through the pair loop (one (xi|ja) block per pole pair and sign);
+ * 1: always on; 2 (default): chosen per call from a flop estimate (it pays when nocc*nvir >> naux). */
+int agf2_b200_set_coulomb_factorization(int mode);
+
 /* Chunks alternate between two CUDA streams (default on) so that the tail of one kernel is filled by the
  * other chain's CTAs.  Switch it off to time k1_form / k2_moment in isolation (agf2_b200_last_kernel_ms). */
 int agf2_b200_set_overlap(int on);

@@ -118,6 +118,24 @@ def test_parity_uhf(lib, shape):
         assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL, (shape, i0, i1, relerr(vv, rv), relerr(vev, rev))
 
 
+def test_coulomb_factorization_on_off(lib):
+    """The Coulomb factorisation (M0/M1 route) and the all-pairs route give the same moments: RHF, RHF slice,
+    SCS, UHF, UHF slice -- each against the oracle with the factorisation on and off."""
+    for on in (True, False):
+        lib.set_coulomb_factorization(on)
+        try:
+            _check_rhf(lib, 9, 27, 150, 37, seed=21)
+            _check_rhf(lib, 9, 27, 150, 37, seed=21, i0=2, i1=7, os_f=1.2, ss_f=1.0 / 3.0)
+            _check_rhf(lib, 3, 140, 70, 150, seed=22)               # naux < one tile, nphys > one tile
+            args = orc.synth_uhf(6, 17, 5, 18, 90, 23, 4)
+            for (i0, i1, os_f, ss_f) in ((0, 6, 1.0, 1.0), (2, 5, 1.2, 1.0 / 3.0), (0, 6, 1.0, 0.0), (1, 6, 0.0, 1.0)):
+                vv, vev = lib.moments_uhf(*args, 23, i0, i1, os_f, ss_f)
+                rv, rev = orc.np_build_part_loop_uhf(*args, 23, 6, 5, 17, 18, 90, i0, i1, os_f, ss_f)
+                assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL, (on, i0, i1, relerr(vv, rv), relerr(vev, rev))
+        finally:
+            lib.set_coulomb_factorization(2)
+
+
 def test_small_workspace_many_chunks(lib):
     """Force many chunks (tiny workspace) -- exercises the chunk loop and tile double-buffering."""
     lib.set_workspace_bytes(1 << 20)

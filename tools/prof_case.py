@@ -19,7 +19,7 @@ for r in range(reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     vv, vev = lib.moments_rhf_dev(ixq, qja, ei, ea, sync=True)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    k1, k2 = lib.last_kernel_ms()
-    print("shape %s: %.4f s, %.2f TF/s alg | k1 %.2f ms (%.2f TF/s) k2 %.2f ms (%.2f TF/s alg) | launches %d | checksum %.6e"
+    k1, k2, km, kc = lib.last_stage_ms()
+    print("shape %s: %.4f s, %.2f TF/s alg | k1 %.2f ms (%.2f TF/s) k2 %.2f ms (%.2f TF/s alg) | M %.2f ms, coulomb %.2f ms | launches %d | checksum %.6e"
           % ((o, v, n, p), dt, falg / dt * 1e-12, k1, 2.0 * p * o * o * v * n / k1 * 1e-9, k2,
-             4.0 * p * p * o * o * v / k2 * 1e-9, lib.launch_count(reset=True), float(vv.sum())))
+             4.0 * p * p * o * o * v / k2 * 1e-9, km, kc, lib.launch_count(reset=True), float(vv.sum())))
