@@ -102,6 +102,7 @@ struct Ctx {
     int64_t chunk_counter = 0;
     std::vector<EventPair> events;
     size_t events_used = 0;
+    int64_t last_plan[6] = {0, 0, 0, 0, 0, 0};   // factorised, PAIR, DIAG, OS, ASYM items, k1_form launches
     double last_ms[4] = {0, 0, 0, 0};   // k1_form, k2_moment (pairs), M build, Coulomb step (DGEMM + k2)
 };
 Ctx g_ctx;
@@ -536,6 +537,11 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
         sym_items.insert(sym_items.end(), diag_items.begin(), diag_items.end());
         sym_items.insert(sym_items.end(), os_items.begin(), os_items.end());
     }
+    c.last_plan[0] = fact ? 1 : 0;
+    c.last_plan[1] = c.last_plan[2] = c.last_plan[3] = 0;
+    for (const Item& it : sym_items) c.last_plan[it.kind == 1 ? 1 : (it.kind == 0 ? 2 : 3)]++;
+    c.last_plan[4] = (int64_t)asym_items.size();
+    c.last_plan[5] = 0;
     const std::vector<std::pair<int, int>> blk_same = split_blocks(vpad, c.balanced_blocks);
     const std::vector<std::pair<int, int>> blk_other = split_blocks(vbpad, c.balanced_blocks);
     // items per chunk, per kind (0 = not yet chosen)
@@ -731,6 +737,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaEventRecord(c.t1_free[buf], sc));
             c.launches++;
+            c.last_plan[5]++;
 
             // ---- K2: accumulate the moments of this chunk ----
             const std::vector<K2Tile>& t2 = sym ? t2_sym : t2_all;
@@ -902,6 +909,12 @@ int agf2_b200_last_stage_ms(double* ms4) {
     return 0;
 }
 
+int agf2_b200_last_plan(int64_t* info6) {
+    if (!info6) return fail(AGF2_B200_EINVAL, "null pointer");
+    for (int k = 0; k < 6; ++k) info6[k] = g_ctx.last_plan[k];
+    return 0;
+}
+
 int agf2_b200_set_coulomb_factorization(int mode) {
     if (mode < 0 || mode > 2) return fail(AGF2_B200_EINVAL, "mode must be 0 (off), 1 (always) or 2 (automatic)");
     g_ctx.coulomb = mode != 0;
@@ -989,6 +1002,15 @@ int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const do
                                   int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t istart,
                                   int64_t iend, double os_factor, double ss_factor, double* vv, double* vev)
 {
+    return agf2_b200_build_part_loop_rhf_sharded(ixq, qja, ei, ea, nphys, nocc, nvir, naux, istart, iend, os_factor,
+                                                 ss_factor, 0, 1, vv, vev);
+}
+
+int agf2_b200_build_part_loop_rhf_sharded(const double* ixq, const double* qja, const double* ei, const double* ea,
+                                          int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t istart,
+                                          int64_t iend, double os_factor, double ss_factor, int64_t part,
+                                          int64_t nparts, double* vv, double* vev)
+{
     if (int r = ensure_ctx()) return r;
     if (!ixq || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
     if (nphys <= 0 || nocc <= 0 || nvir <= 0 || naux <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
@@ -1006,7 +1028,7 @@ int agf2_b200_build_part_loop_rhf(const double* ixq, const double* qja, const do
     Uploader up;      // ixq streams in pole by pole while the first pairs are already being processed
     if (int r = up.start(ixq, 0, nocc, nphys, naux, istart, iend, &ld_ixq)) return r;
     int r = moments_rhf_impl(c.stage[0], ld_ixq, c.stage[1], ld_qja, c.stage[2], c.stage[3], nphys, nocc, nvir,
-                             naux, istart, iend, os_factor, ss_factor, 0, 1, dvv, dvev, st, 1, &up.g);
+                             naux, istart, iend, os_factor, ss_factor, part, nparts, dvv, dvev, st, 1, &up.g);
     up.join();
     if (r) return r;
     std::vector<double> h((size_t)2 * nphys * nphys);
@@ -1021,6 +1043,17 @@ int agf2_b200_build_part_loop_uhf(const double* ixq_a, const double* qja_a, cons
                                   int64_t nocc_a, int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
                                   int64_t istart, int64_t iend, double os_factor, double ss_factor, double* vv,
                                   double* vev)
+{
+    return agf2_b200_build_part_loop_uhf_sharded(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a, nocc_b,
+                                                 nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor, 0, 1, vv, vev);
+}
+
+int agf2_b200_build_part_loop_uhf_sharded(const double* ixq_a, const double* qja_a, const double* qja_b,
+                                          const double* ei_a, const double* ei_b, const double* ea_a,
+                                          const double* ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                                          int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart, int64_t iend,
+                                          double os_factor, double ss_factor, int64_t part, int64_t nparts,
+                                          double* vv, double* vev)
 {
     if (int r = ensure_ctx()) return r;
     if (!ixq_a || !qja_a || !ei_a || !ea_a || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
@@ -1047,7 +1080,7 @@ int agf2_b200_build_part_loop_uhf(const double* ixq_a, const double* qja_a, cons
     int r = moments_uhf_impl(c.stage[0], ld_ixq, c.stage[1], ld_qa, has_b ? c.stage[5] : nullptr, ld_qb,
                              c.stage[2], has_b ? c.stage[6] : nullptr, c.stage[3], has_b ? c.stage[7] : nullptr,
                              nphys, nocc_a, has_b ? nocc_b : 0, nvir_a, has_b ? nvir_b : 0, naux, istart, iend,
-                             os_factor, ss_factor, 0, 1, dvv, dvev, st, 1, &up.g);
+                             os_factor, ss_factor, part, nparts, dvv, dvev, st, 1, &up.g);
     up.join();
     if (r) return r;
     std::vector<double> h((size_t)2 * nphys * nphys);

@@ -32,7 +32,8 @@ SYMBOLS = [
     "agf2_b200_build_part_loop_uhf", "agf2_b200_moments_rhf_dev", "agf2_b200_moments_uhf_dev",
     "agf2_b200_compress", "agf2_b200_eigh", "agf2_b200_launch_count", "agf2_b200_last_kernel_ms",
     "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap", "agf2_b200_last_stage_ms",
-    "agf2_b200_set_coulomb_factorization",
+    "agf2_b200_set_coulomb_factorization", "agf2_b200_last_plan", "agf2_b200_build_part_loop_rhf_sharded",
+    "agf2_b200_build_part_loop_uhf_sharded",
 ]
 
 
@@ -63,6 +64,10 @@ _libagf2.agf2_b200_set_device.argtypes = [ctypes.c_int]
 _libagf2.agf2_b200_set_workspace_bytes.argtypes = [_i64]
 _libagf2.agf2_b200_set_simple_kernels.argtypes = [ctypes.c_int]
 _libagf2.agf2_b200_build_part_loop_rhf.argtypes = [_in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_build_part_loop_rhf_sharded.argtypes = [_in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _i64, _i64,
+                                                                                                _out2, _out2]
+_libagf2.agf2_b200_build_part_loop_uhf_sharded.argtypes = [_in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_i64] * 8 + \
+    [_dbl, _dbl, _i64, _i64, _out2, _out2]
 _libagf2.agf2_b200_build_part_loop_uhf.argtypes = [_in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_i64] * 8 + \
     [_dbl, _dbl, _out2, _out2]
 _libagf2.agf2_b200_moments_rhf_dev.argtypes = [_vp, _i64, _vp, _i64, _vp, _vp] + [_i64] * 6 + [_dbl, _dbl, _i64, _i64,
@@ -110,6 +115,13 @@ def last_stage_ms():
     return tuple(out)
 
 
+def last_plan():
+    """Plan of the last moments call: dict(factorised, pair, diag, os, asym, k1_launches)."""
+    out = (_i64 * 6)()
+    check(_libagf2.agf2_b200_last_plan(out))
+    return dict(zip(("factorised", "pair", "diag", "os", "asym", "k1_launches"), [int(x) for x in out]))
+
+
 def set_coulomb_factorization(mode):
     """0 / False: off, 1 / True: always, 2: automatic (default)."""
     check(_libagf2.agf2_b200_set_coulomb_factorization(int(mode)))
@@ -130,7 +142,7 @@ def _c(a, ndim):
 
 
 def build_part_loop_rhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None,
-                        os_factor=1.0, ss_factor=1.0):
+                        os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
     """Inner loop of ``OptRAGF2.build_part`` on the GPU (signature of auxgf/lib/agf2.py:63)."""
     nocc = gf_occ.naux
     nvir = gf_vir.naux
@@ -150,13 +162,13 @@ def build_part_loop_rhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=Non
     vv = np.ascontiguousarray(vv)
     vev = np.ascontiguousarray(vev)
 
-    check(_libagf2.agf2_b200_build_part_loop_rhf(ixq, qja, ei, ea, nphys, nocc, nvir, naux, istart, iend,
-                                                 os_factor, ss_factor, vv, vev))
+    check(_libagf2.agf2_b200_build_part_loop_rhf_sharded(ixq, qja, ei, ea, nphys, nocc, nvir, naux, istart, iend,
+                                                         os_factor, ss_factor, part, nparts, vv, vev))
     return vv, vev
 
 
 def build_part_loop_uhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None,
-                        os_factor=1.0, ss_factor=1.0):
+                        os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
     """Inner loop of ``OptUAGF2.build_part`` for one spin channel (auxgf/lib/agf2.py:102)."""
     nocc_a = gf_occ[0].naux
     nocc_b = gf_occ[1].naux
@@ -181,8 +193,9 @@ def build_part_loop_uhf(ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=Non
     vv = np.ascontiguousarray(vv)
     vev = np.ascontiguousarray(vev)
 
-    check(_libagf2.agf2_b200_build_part_loop_uhf(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a, nocc_b,
-                                                 nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor, vv, vev))
+    check(_libagf2.agf2_b200_build_part_loop_uhf_sharded(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, nocc_a,
+                                                         nocc_b, nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor,
+                                                         part, nparts, vv, vev))
     return vv, vev
 
 
@@ -194,10 +207,10 @@ class _Poles:
         self.nphys = nphys
 
 
-def moments_rhf(ixq, qja, ei, ea, nphys, istart=0, iend=None, os_factor=1.0, ss_factor=1.0):
+def moments_rhf(ixq, qja, ei, ea, nphys, istart=0, iend=None, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
     occ, vir = _Poles(ei, nphys), _Poles(ea, nphys)
     return build_part_loop_rhf(ixq, qja, occ, vir, istart, occ.naux if iend is None else iend,
-                               os_factor=os_factor, ss_factor=ss_factor)
+                               os_factor=os_factor, ss_factor=ss_factor, part=part, nparts=nparts)
 
 
 def moments_uhf(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, istart=0, iend=None,

@@ -12,9 +12,10 @@ auxgf/agf2/optragf2.py:283-293), F_alg = 1.50e15 flop.
   value    : seconds per moment build with the DF tensors already resident in HBM (device C-ABI)
   e2e      : the same build through the reference-facing host-pointer C-ABI
              (agf2_b200_build_part_loop_rhf: host ixq/qja in, host vv/vev out, copies in the timed region)
-  roofline : dominant kernel k1_form (integral formation), algorithmic FP64 flop / summed launch time
-             measured with CUDA events, against the cuBLAS DGEMM peak measured on this pool's B200
-             (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json carries no FP64 figure)
+  roofline : dominant kernel k1_form (integral formation): algorithmic FP64 flop of the (xi|ja) blocks the
+             launches form (4 P nvir naux per pole pair) / summed launch time measured with CUDA events,
+             against the cuBLAS DGEMM peak measured on this pool's B200 (profiles/fp64_peak_r01.json;
+             MEASURED_PEAKS.json carries no FP64 figure)
   cpu_baseline / --impl reference : the reference's own C loop (oracle/_ref/agf2.so, built from
              /root/reference/auxgf/lib/libagf2) on the host cores, on a bounded slice of poles,
              scaled to one build.
@@ -107,7 +108,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU reference leg (oracle/_ref = the reference's own C loop; else the NumPy port)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_sample(o, v, n, p, budget_s=20.0):
+def cpu_reference_sample(o, v, n, p, budget_s=20.0, keep=None):
     """Times the reference loop on a slice of occupied poles of the occupied-sector call and scales by
     executed work to one full build (work per pole is identical in both sectors: 4PovN + 8P^2ov)."""
     from oracle import agf2_oracle as orc
@@ -136,7 +137,9 @@ def cpu_reference_sample(o, v, n, p, budget_s=20.0):
         fn = lambda i0, i1: orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, i0, i1)  # noqa: E731
     t0 = time.perf_counter(); fn(0, omp); t1 = time.perf_counter() - t0        # warm + calibrate
     ni = int(max(omp, min(o, omp * max(1, int(budget_s / max(t1, 1e-3))))))
-    t0 = time.perf_counter(); fn(0, ni); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); res = fn(0, ni); dt = time.perf_counter() - t0
+    if keep is not None:     # inputs + result of the timed slice, for the full-size parity check of the GPU path
+        keep.update(ixq=ixq, qja=qja, ei=ei, ea=ea, ni=ni, vv=res[0], vev=res[1])
     per_pole = dt / ni
     build_s = per_pole * (o + v)          # o poles in the occupied sector + v poles in the virtual one
     return {"value": build_s, "unit": "s", "cores": threads, "kind": kind,
@@ -247,22 +250,29 @@ def main():
     # two-stream chunk overlap switched off so that each launch is timed alone on the GPU
     lib.set_overlap(False)
     lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, sync=True)
-    a1, b1 = lib.last_kernel_ms()
+    st1, pl1 = lib.last_stage_ms(), lib.last_plan()
     lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, sync=True)
-    a2, b2 = lib.last_kernel_ms()
+    st2, pl2 = lib.last_stage_ms(), lib.last_plan()
     lib.set_overlap(True)
-    k1_ms, k2_ms = a1 + a2, b1 + b2
-    prof_launches = lib.launch_count()
+    k1_ms, k2_ms, m_ms, c_ms = [a + b for a, b in zip(st1, st2)]
+    # (xi|ja) blocks formed by k1_form on this rank: two per PAIR / ASYM item, one per DIAG / OS item
+    k1_blocks = [2 * (pl["pair"] + pl["asym"]) + pl["diag"] + pl["os"] for pl in (pl1, pl2)]
+    k1_flops_rank = 2.0 * p * n * (k1_blocks[0] * v + k1_blocks[1] * o)
+    k1_launches = pl1["k1_launches"] + pl2["k1_launches"]
 
-    # ------------------------------------------------------------------ e2e (host buffers, rank 0, N=1)
+    # ------------------------------------------------------------------ e2e (host buffers, every rank)
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         host_gb = (ixq_o.numel() + qja_o.numel() + ixq_v.numel() + qja_v.numel()) * 8 / 1e9
         try:
             avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 1e9
         except Exception:
             avail_gb = 0.0
-        if avail_gb > host_gb * 1.3 + 8:
+        need_gb = host_gb * 1.3 * world + 8          # every rank of the node holds its own host copy
+        ok = torch.tensor([1.0 if avail_gb > need_gb else 0.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() > 0:
             h = [ixq_o.cpu().numpy().reshape(o * p, n), qja_o.cpu().numpy().reshape(n, o * v),
                  ixq_v.cpu().numpy().reshape(v * p, n), qja_v.cpu().numpy().reshape(n, v * o)]
             eo_h, ev_h = e_o.cpu().numpy(), e_v.cpu().numpy()
@@ -270,24 +280,39 @@ def main():
             torch.cuda.empty_cache()
 
             def host_step():
-                r0 = lib.moments_rhf(h[0], h[1], eo_h, ev_h, p)
-                r1 = lib.moments_rhf(h[2], h[3], ev_h, eo_h, p)
-                return r0, r1
+                # the call a user of the reference makes: host DF blocks in, host vv/vev out (per rank: its share
+                # of the pair-work items), then the one all-reduce of [vv|vev] over the ranks
+                r0 = lib.moments_rhf(h[0], h[1], eo_h, ev_h, p, part=rank, nparts=world)
+                r1 = lib.moments_rhf(h[2], h[3], ev_h, eo_h, p, part=rank, nparts=world)
+                res = np.stack([r0[0], r0[1], r1[0], r1[1]]).reshape(2, 2, p, p)
+                if world > 1:
+                    buf = torch.from_numpy(res).to(dev)
+                    dist.all_reduce(buf)
+                    res = buf.cpu().numpy()
+                return res
             host_step()
+            n_e2e = max(1, min(args.steps, 2))
+            sync_all()
             t0 = time.perf_counter()
-            for _ in range(max(1, min(args.steps, 2))):
+            for _ in range(n_e2e):
                 res = host_step()
-            dt = (time.perf_counter() - t0) / max(1, min(args.steps, 2))
-            chk2 = float(sum(a.sum() for r in res for a in r))
-            dev_vs_host = max(float(np.abs(res[k][m] - out_host[k, m]).max() / np.abs(out_host[k, m]).max())
+            sync_all()
+            dt_t = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+            dt = float(dt_t.item())
+            chk2 = float(res.sum())
+            dev_vs_host = max(float(np.abs(res[k, m] - out_host[k, m]).max() / np.abs(out_host[k, m]).max())
                               for k in range(2) for m in range(2))
-            e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v),
-                   "d2h_bytes_per_step": 4 * p * p * 8, "tflops": flops_build / dt * 1e-12,
+            red = 4 * p * p * 8 if world > 1 else 0
+            e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v) + red,
+                   "d2h_bytes_per_step": 4 * p * p * 8 + red, "bytes_are": "per rank", "tflops": flops_build / dt * 1e-12,
                    "checksum_rel_diff_vs_device_path": abs(chk2 - checksum) / max(abs(checksum), 1e-300),
                    "max_rel_diff_vs_device_path": dev_vs_host,
-                   "api": "agf2_b200_build_part_loop_rhf (host pointers, pageable NumPy buffers)"}
+                   "api": "agf2_b200_build_part_loop_rhf_sharded (host pointers, pageable NumPy buffers; "
+                          "ixq upload pipelined under the pair loop)"}
         else:
-            e2e = {"value": None, "unit": "s", "skipped": "host RAM %.0f GB < %.0f GB needed for the host copies" % (avail_gb, host_gb * 1.3 + 8)}
+            e2e = {"value": None, "unit": "s", "skipped": "host RAM %.0f GB < %.0f GB needed for the host copies" % (avail_gb, need_gb)}
 
     if rank != 0:
         if world > 1:
@@ -295,22 +320,22 @@ def main():
         return 0
 
     peak, peak_src = fp64_peak()
-    traffic = None
+    traffic = traffic_note = None
     try:   # DRAM bytes of one k1_form launch from the committed `ncu --set full` capture
         import csv
         with open(os.path.join(ROOT, "profiles", "r01_k1_form_ncu.csv")) as f:
-            m = {r[2]: (float(r[3]), r[4]) for r in csv.reader(f) if r[0] == "0"}
+            rows = [r for r in csv.reader(f) if r and r[0] == "0"]
+        m = {r[2]: (float(r[3]), r[4]) for r in rows}
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
-        traffic = {"bytes_per_launch": rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]],
-                   "launch": "k1_form grid 378 (21 pole pairs of o=64 v=100 naux=4000 nphys=1100), "
-                             "operand bytes of that launch 0.85e9 (22 poles x (ixq 35.2 MB + qja 3.2 MB))",
-                   "source": "profiles/r01_k1_form_ncu.csv"}
+        traffic = rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]]
+        traffic_note = ("dram read+write bytes of one k1_form launch (grid %d) of tools/prof_case.py 64,100,4000,1100, "
+                        "profiles/r01_k1_form_ncu.csv; the path is tensor-bound, the figure only shows that (xi|ja) "
+                        "is not spilled to HBM" % int(m["launch__grid_size"][0]))
     except Exception:
         pass
-    k1_flops = f_k1(o, v, n, p) + f_k1(v, o, n, p)
-    k1_tf = k1_flops / world / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else None
-    k2_flops = flops_build - k1_flops
+    k1_tf = k1_flops_rank / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else None
+    k2_flops = flops_build - (f_k1(o, v, n, p) + f_k1(v, o, n, p))
     line = {
         "metric": "agf2_moment_build_seconds_per_iter", "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
@@ -322,16 +347,31 @@ def main():
         "fp64_peak_tflops": peak, "fp64_peak_source": peak_src,
         "roofline": {"bound": "tensor", "kernel": "k1_form (FP64 DMMA.8x8x4)", "achieved": k1_tf, "peak": peak,
                      "unit": "TFLOP/s", "frac": (k1_tf / peak) if k1_tf else None, "traffic": traffic,
-                     "k1_ms_per_step": k1_ms, "k2_ms_per_step": k2_ms,
-                     "note": "k1/k2 launch times from an extra untimed step with the chunk overlap off (each launch "
-                             "alone on the GPU); the timed steps overlap the two kernels on two streams",
-                     "k2_achieved": k2_flops / world / (k2_ms * 1e-3) * 1e-12 if k2_ms > 0 else None},
+                     "traffic_note": traffic_note,
+                     "launches_per_step": k1_launches, "blocks_per_step": sum(k1_blocks),
+                     "flop_per_block": "2 * nphys * nvir * naux (one (xi|ja) block of one pole pair)",
+                     "k1_ms_per_step": k1_ms, "k2_ms_per_step": k2_ms, "m_build_ms_per_step": m_ms,
+                     "coulomb_ms_per_step": c_ms, "coulomb_factorised": [bool(pl1["factorised"]), bool(pl2["factorised"])],
+                     "note": "stage times from an extra untimed step with the chunk overlap off (each launch alone "
+                             "on the GPU); the timed steps overlap the two chunk chains on two streams",
+                     "moment_stage_achieved": k2_flops / world / ((k2_ms + m_ms + c_ms) * 1e-3) * 1e-12
+                     if k2_ms > 0 else None},
         "gpu_launches": int(launches), "clocks": clocks, "checksum": checksum,
     }
     if e2e is not None:
         line["e2e"] = e2e
     if not args.no_cpu and world == 1:
-        line["cpu_baseline"] = cpu_reference_sample(o, v, n, p, budget_s=args.cpu_budget)
+        keep = {}
+        cb = cpu_reference_sample(o, v, n, p, budget_s=args.cpu_budget, keep=keep)
+        try:    # full-size parity: the same pole slice of the same inputs through the host-pointer C-ABI
+            g = lib.moments_rhf(keep["ixq"], keep["qja"], keep["ei"], keep["ea"], p, 0, keep["ni"])
+            cb["parity_max_rel_diff"] = max(float(np.abs(g[k] - keep[nm]).max() / np.abs(keep[nm]).max())
+                                            for k, nm in enumerate(("vv", "vev")))
+            cb["parity_note"] = "GPU vs CPU reference on poles [0,%d) of the occupied-sector call at full size" % keep["ni"]
+        except Exception as e:   # noqa: BLE001
+            cb["parity_max_rel_diff"] = None
+            cb["parity_note"] = "not checked: %s" % e
+        line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -92,6 +92,22 @@ int agf2_b200_build_part_loop_uhf(const double *ixq_a, const double *qja_a, cons
                                   int64_t istart, int64_t iend, double os_factor,
                                   double ss_factor, double *vv, double *vev);
 
+/* The same two calls restricted to the pair-work items [part, nparts) (see the device-resident variants below):
+ * one call per GPU / process, the caller sums the per-part vv/vev (replaces the per-rank [istart, iend) slices and
+ * Reduce + Bcast of auxgf/mpi/agf2/optragf2.py:370-395 without the cost of non-symmetric slices). */
+int agf2_b200_build_part_loop_rhf_sharded(const double *ixq, const double *qja, const double *ei,
+                                          const double *ea, int64_t nphys, int64_t nocc, int64_t nvir,
+                                          int64_t naux, int64_t istart, int64_t iend, double os_factor,
+                                          double ss_factor, int64_t part, int64_t nparts, double *vv,
+                                          double *vev);
+
+int agf2_b200_build_part_loop_uhf_sharded(const double *ixq_a, const double *qja_a, const double *qja_b,
+                                          const double *ei_a, const double *ei_b, const double *ea_a,
+                                          const double *ea_b, int64_t nphys, int64_t nocc_a, int64_t nocc_b,
+                                          int64_t nvir_a, int64_t nvir_b, int64_t naux, int64_t istart,
+                                          int64_t iend, double os_factor, double ss_factor, int64_t part,
+                                          int64_t nparts, double *vv, double *vev);
+
 /* Device-resident variants: every pointer is DEVICE memory on the selected device.
  *   ixq : (nocc, nphys, ld_ixq) with ld_ixq >= naux, ld_ixq even   (row pitch in doubles)
  *   qja : (naux, nocc, ld_qja)  with ld_qja >= nvir, ld_qja even
@@ -159,6 +175,11 @@ int agf2_b200_last_kernel_ms(double *k1_form_ms, double *k2_moment_ms);
 /* Device time (ms) of the last moments call by stage: [0] k1_form, [1] k2_moment of the pair loop, [2] the
  * M0/M1 build and [3] the T = ixq M DGEMMs + moment accumulation of the Coulomb factorisation. */
 int agf2_b200_last_stage_ms(double *ms4);
+
+/* Plan of the last moments call: [0] Coulomb factorisation used, work items of this part by kind -- [1] PAIR (i>j: two
+ * (xi|ja) blocks each), [2] DIAG, [3] OS (one block each), [4] ASYM (j outside the slice: two blocks) -- and
+ * [5] the number of k1_form launches (= chunks). */
+int agf2_b200_last_plan(int64_t *info6);
 
 /* Coulomb factorisation (default on): every Coulomb-type term  sum_ija w X_ija X_ija^T (e_i+e_j-e_a)^n  of
  * auxgf/lib/libagf2/optragf2.c:206-290 / optuagf2.c:211-314 is evaluated as  sum_i ixq_i (e_i^n M0 + n M1) ixq_i^T
