@@ -83,6 +83,7 @@ struct Ctx {
     int* d_cost = nullptr;             // stream-K cost prefixes of the K2 tile lists
     size_t cost_cap = 0;
     // Coulomb factorisation scratch: M = [M0 | M1], T = ixq_batch . M, per-column weights
+    bool thin_tiles = true;            // last x-block with <= 80 valid rows uses the thin-tile mapping of k1_form
     bool coulomb = true;               // Coulomb factorisation allowed ...
     bool coulomb_auto = true;          // ... and chosen per call by a flop estimate (false: always when allowed)
     int k2_mask = 1;                   // edge tiles of k2_moment skip the column blocks they do not need
@@ -148,6 +149,7 @@ int ensure_ctx() {
     if (const char* e = getenv("AGF2_B200_TUNE_CHUNK")) c.tune_chunk = atoi(e) != 0;
     if (const char* e = getenv("AGF2_B200_COULOMB")) { c.coulomb = atoi(e) != 0; c.coulomb_auto = atoi(e) == 2; }
     if (const char* e = getenv("AGF2_B200_K2_MASK")) c.k2_mask = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_THIN")) c.thin_tiles = atoi(e) != 0;
     if (cublasCreate(&c.blas) != CUBLAS_STATUS_SUCCESS) return fail(AGF2_B200_ESOLVER, "cublasCreate failed");
     c.init = true;
     return 0;
@@ -544,6 +546,17 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     c.last_plan[5] = 0;
     const std::vector<std::pair<int, int>> blk_same = split_blocks(vpad, c.balanced_blocks);
     const std::vector<std::pair<int, int>> blk_other = split_blocks(vbpad, c.balanced_blocks);
+    // thin-tile mapping of the last x-block (k1_mainloop_thin): number of valid 8-row blocks, 0 = full tile
+    auto thin_mbv = [&](int xb, int nb1, int nb2) -> int {
+        if (!c.thin_tiles || c.simple || xb != nxb - 1) return 0;
+        const int mbv = (int)((nphys - (int64_t)xb * kTileM + 7) / 8);
+        if (mbv > 10) return 0;
+        const int nsets = (nb1 > 0) + (nb2 > 0);
+        return (1.15 * mbv * nsets < 2.0 * (nb1 + nb2)) ? mbv : 0;   // per-warp DMMA count: thin vs full
+    };
+    auto tile_work = [](const K1Tile& t) -> int {   // per-warp DMMAs per k-step (x 2): the tile's duration
+        return t.mbv > 0 ? t.mbv * ((t.nb1 > 0) + (t.nb2 > 0)) : 2 * (t.nb1 + t.nb2);
+    };
     // items per chunk, per kind (0 = not yet chosen)
     int chunk_items[4] = {0, 0, 0, 0};
     auto items_per_chunk = [&](int kind) -> int {
@@ -559,11 +572,17 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
             const auto& blks = kind == 2 ? blk_other : blk_same;
             if (kind == 1 || kind == 3) {
                 for (int xb = 0; xb < nxb; ++xb)
-                    for (auto& b : blks) t.push_back(2.0 * b.second + ovh);
+                    for (auto& b : blks) {
+                        const int mbv = thin_mbv(xb, b.second, b.second);
+                        t.push_back((mbv ? (double)mbv : 2.0 * b.second) + ovh);
+                    }
             } else {
                 // plain blocks pair up two by two across items: model one item as half-tiles
                 for (int xb = 0; xb < nxb; ++xb)
-                    for (auto& b : blks) t.push_back(b.second + 0.5 * ovh);
+                    for (auto& b : blks) {
+                        const int mbv = thin_mbv(xb, b.second, b.second);
+                        t.push_back((mbv ? 0.5 * mbv : (double)b.second) + 0.5 * ovh);
+                    }
             }
             n = pick_chunk_items(t, n_max, c.num_sms, c.lpt_order, 0.5);
         }
@@ -639,6 +658,7 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                                 t.ws1 = 0; t.p11 = 1.0; t.p12 = 0.0;
                                 t.ws2 = 1; t.p21 = asym_c; t.p22 = -s_same;   // (p21 = 0: out2 width falls back to nb2 == nb1)
                             }
+                            t.mbv = thin_mbv(xb, t.nb1, t.nb2);
                             tiles.push_back(t);
                         }
                     }
@@ -676,13 +696,14 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
                         t.i2 = s2->i; t.j2 = s2->j; t.a2 = s2->a0; t.nb2 = s2->nb; t.bsel2 = s2->bsel; t.esel2 = s2->esel;
                         t.nv2 = s2->nv; t.col2 = s2->col; t.p22 = s2->p; t.e2 = s2->eij; t.ws2 = 0;
                     }
+                    t.mbv = thin_mbv(xb, t.nb1, t.nb2);
                     tiles.push_back(t);
                 }
             }
             // longest tiles first: the block scheduler then packs the short ones into the tail of the launch
             if (c.lpt_order)
                 std::stable_sort(tiles.begin(), tiles.end(),
-                                 [](const K1Tile& a, const K1Tile& b) { return a.nb1 + a.nb2 > b.nb1 + b.nb2; });
+                                 [&](const K1Tile& a, const K1Tile& b) { return tile_work(a) > tile_work(b); });
 
             // ---- upload the tile list (double-buffered pinned staging) ----
             const int buf = (int)(chunk_idx & 1);

@@ -46,6 +46,8 @@ struct K1Tile {
     long long col1, col2;  // destination column of out1 / out2
     double p11, p12, p21, p22;
     double e1, e2;         // e_i + e_j of out1 / out2
+    int mbv;               // > 0: thin tile -- only the first mbv 8-row blocks of the x-block exist (see k1_mainloop_thin)
+    int pad_;
 };
 
 constexpr int kK1StageBytes = 2 * kTileM * kKB * 8 + 2 * kTileN * kKB * 8;  // 49152
@@ -147,6 +149,135 @@ __device__ __forceinline__ void k1_mainloop(const uint8_t* __restrict__ gbase, u
     }
 }
 
+// energy weights E[col] = e_i + e_j - e_a (only the xb == 0 tile of each block writes them; only workspace 0
+// carries weights -- k2 scales its A operand, which always comes from W0)
+__device__ __forceinline__ void k1_write_weights(const K1Tile& t, int warp, int gid, int tig,
+                                                 const double* __restrict__ ea0, const double* __restrict__ ea1,
+                                                 double* __restrict__ E0)
+{
+    if (t.xb == 0 && warp == 0 && gid == 0) {
+        const int nb1 = t.nb1, nb2 = t.nb2;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 8 * nb + 2 * tig + h;
+                if (t.ws1 == 0 && nb < nb1) {
+                    const double* ea = t.esel1 ? ea1 : ea0;
+                    E0[t.col1 + c] = (c < t.nv1) ? (t.e1 - ea[t.a1 + c]) : 0.0;
+                }
+                const int nbo2 = (t.p21 != 0.0) ? nb1 : nb2;
+                if (t.ws2 == 0 && nb < nbo2) {
+                    const double* ea = t.esel2 ? ea1 : ea0;
+                    const int a0 = (t.p21 != 0.0) ? t.a1 : t.a2;
+                    E0[t.col2 + c] = (c < t.nv2) ? (t.e2 - ea[a0 + c]) : 0.0;
+                }
+            }
+        }
+    }
+}
+
+// Thin tile: the last x-block of a shape whose nphys is not a multiple of 128 holds only MBV <= 10 valid 8-row
+// blocks.  Here warp w takes column block w of both integral blocks and ALL row blocks (instead of 16 rows and all
+// column blocks), so the tile costs MBV / (nb1 + nb2) of a full one instead of the same.  One pipeline stage =
+// 4 units (ks, set); the fragments of unit u+1 (the other set) are loaded while unit u's DMMAs issue.
+template <int MBV>
+__device__ __forceinline__ void k1_mainloop_thin(const uint8_t* __restrict__ gbase, uint32_t bar_full, uint32_t bar_empty,
+                                                 int nk, int warp, int lane, bool act1, bool act2,
+                                                 double (&acc1)[MBV][2], double (&acc2)[MBV][2])
+{
+    const int gid = lane >> 2, tig = lane & 3;
+    const int pg = pi8(gid);
+    const uint32_t a_off[2] = {(uint32_t)(pg * 128 + (((tig) ^ pg) << 4)), (uint32_t)(pg * 128 + (((4 + tig) ^ pg) << 4))};
+    uint32_t b_off[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int r = 2 * tig + e;
+        const int chunk = 4 * (warp & 1) + (gid >> 1);
+        b_off[e] = (uint32_t)(r * 128 + ((chunk ^ r) << 4) + (gid & 1) * 8 + (warp >> 1) * 2048);
+    }
+    double2 fa[2][MBV];   // [set][mb]
+    double fb[2][2];      // [set][e]
+    auto load_unit = [&](const uint8_t* st, int u) {
+        const int ks = u >> 1, set = u & 1;
+        if (set ? act2 : act1) {
+#pragma unroll
+            for (int mb = 0; mb < MBV; ++mb)
+                fa[set][mb] = *reinterpret_cast<const double2*>(st + set * 16384 + a_off[ks] + mb * 1024);
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                fb[set][e] = *reinterpret_cast<const double*>(st + 32768 + set * 8192 + b_off[e] + ks * 1024);
+        }
+    };
+    auto compute_unit = [&](int u) {
+        const int set = u & 1;
+        if (set ? act2 : act1) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int mb = 0; mb < MBV; ++mb) {
+                    const double a = e ? fa[set][mb].y : fa[set][mb].x;
+                    if (set) dmma884(acc2[mb][0], acc2[mb][1], a, fb[set][e]);
+                    else dmma884(acc1[mb][0], acc1[mb][1], a, fb[set][e]);
+                }
+        }
+    };
+    mbar_wait(bar_full, 0);
+    load_unit(gbase, 0);
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % kK1Stages;
+        const uint8_t* st = gbase + s * kK1StageBytes;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < 3) {
+                load_unit(st, u + 1);
+            } else if (it + 1 < nk) {
+                const int s2 = (it + 1) % kK1Stages;
+                mbar_wait(bar_full + 8 * s2, ((it + 1) / kK1Stages) & 1);
+                load_unit(gbase + s2 * kK1StageBytes, 0);
+            }
+            compute_unit(u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+}
+
+// thin-tile main loop + fused epilogue for one compile-time row-block count
+template <int MBV>
+__device__ __forceinline__ void k1_thin_tile(const K1Tile& t, const uint8_t* __restrict__ gbase, uint32_t bar_full,
+                                             uint32_t bar_empty, int nk, int warp, int lane, double* __restrict__ W0,
+                                             double* __restrict__ W1, long long ldw)
+{
+    const int gid = lane >> 2, tig = lane & 3;
+    const int pg = pi8(gid);
+    double acc1[MBV][2], acc2[MBV][2];
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb) { acc1[mb][0] = acc1[mb][1] = 0.0; acc2[mb][0] = acc2[mb][1] = 0.0; }
+    const bool act1 = warp < t.nb1, act2 = warp < t.nb2;
+    k1_mainloop_thin<MBV>(gbase, bar_full, bar_empty, nk, warp, lane, act1, act2, acc1, acc2);
+    double* const Wd1 = t.ws1 == 0 ? W0 : (t.ws1 == 1 ? W1 : nullptr);
+    double* const Wd2 = t.ws2 == 0 ? W0 : (t.ws2 == 1 ? W1 : nullptr);
+    const int nbo2 = (t.p21 != 0.0) ? t.nb1 : t.nb2;
+    const int c = 8 * warp + 2 * tig;
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb) {
+        const long long row = (long long)t.xb * kTileM + 8 * mb + pg;
+        if (Wd1 != nullptr && act1) {
+            double2 o;
+            o.x = t.p11 * acc1[mb][0] + t.p12 * acc2[mb][0];
+            o.y = t.p11 * acc1[mb][1] + t.p12 * acc2[mb][1];
+            *reinterpret_cast<double2*>(Wd1 + row * ldw + t.col1 + c) = o;
+        }
+        if (Wd2 != nullptr && warp < nbo2) {
+            double2 o;
+            o.x = t.p21 * acc1[mb][0] + t.p22 * acc2[mb][0];
+            o.y = t.p21 * acc1[mb][1] + t.p22 * acc2[mb][1];
+            *reinterpret_cast<double2*>(Wd2 + row * ldw + t.col2 + c) = o;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
         const __grid_constant__ CUtensorMap mapB1, const K1Tile* __restrict__ tiles,
@@ -204,9 +335,20 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
     }
     reg_alloc_consumer();
 
-    // ===== consumers: 8 warps x (16 rows x 64 cols x 2 blocks) =====
+    // ===== consumers: 8 warps x (16 rows x 64 cols x 2 blocks), or the thin-tile mapping =====
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
+    if (t.mbv > 0) {
+        switch (t.mbv) {
+#define AGF2_K1_THIN(M) case M: k1_thin_tile<M>(t, gbase, bar_full, bar_empty, nk, warp, lane, W0, W1, ldw); break;
+            AGF2_K1_THIN(1) AGF2_K1_THIN(2) AGF2_K1_THIN(3) AGF2_K1_THIN(4) AGF2_K1_THIN(5)
+            AGF2_K1_THIN(6) AGF2_K1_THIN(7) AGF2_K1_THIN(8) AGF2_K1_THIN(9) AGF2_K1_THIN(10)
+#undef AGF2_K1_THIN
+            default: __trap();
+        }
+        k1_write_weights(t, warp, gid, tig, ea0, ea1, E0);
+        return;
+    }
     double acc1[2][8][2], acc2[2][8][2];
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
@@ -251,27 +393,7 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
             }
         }
     }
-    // energy weights E[col] = e_i + e_j - e_a (only the xb == 0 tile of each block writes them;
-    // only workspace 0 carries weights -- k2 scales its A operand, which always comes from W0)
-    if (t.xb == 0 && warp == 0 && gid == 0) {
-#pragma unroll
-        for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = 8 * nb + 2 * tig + h;
-                if (t.ws1 == 0 && nb < nb1) {
-                    const double* ea = t.esel1 ? ea1 : ea0;
-                    E0[t.col1 + c] = (c < t.nv1) ? (t.e1 - ea[t.a1 + c]) : 0.0;
-                }
-                const int nbo2 = (t.p21 != 0.0) ? nb1 : nb2;
-                if (t.ws2 == 0 && nb < nbo2) {
-                    const double* ea = t.esel2 ? ea1 : ea0;
-                    const int a0 = (t.p21 != 0.0) ? t.a1 : t.a2;
-                    E0[t.col2 + c] = (c < t.nv2) ? (t.e2 - ea[a0 + c]) : 0.0;
-                }
-            }
-        }
-    }
+    k1_write_weights(t, warp, gid, tig, ea0, ea1, E0);
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------

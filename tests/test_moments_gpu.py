@@ -74,6 +74,27 @@ def test_parity_ladder_rhf(lib, shape):
     _check_rhf(lib, o, v, n, p, seed=1)
 
 
+def test_thin_tiles(lib):
+    """Last x-block with 1..10 valid 8-row blocks (k1_mainloop_thin<1..10>), alone (nphys < 128: it also writes
+    the energy weights) and behind a full x-block; wide and narrow column blocks; slice; UHF."""
+    for mbv in range(1, 11):
+        _check_rhf(lib, 4, 70, 50, 8 * mbv - 3, seed=30 + mbv)
+    for p in (128 + 5, 128 + 44, 256 + 77, 128 + 80):
+        _check_rhf(lib, 5, 130, 90, p, seed=41)
+    _check_rhf(lib, 6, 64, 40, 140, seed=42, i0=1, i1=4, os_f=1.2, ss_f=1.0 / 3.0)
+    args = orc.synth_uhf(5, 66, 4, 71, 60, 150, 5)
+    vv, vev = lib.moments_uhf(*args, 150)
+    rv, rev = orc.np_build_part_loop_uhf(*args, 150, 5, 4, 66, 71, 60, 0, 5)
+    assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL
+    lib.set_coulomb_factorization(0)      # DIAG / OS items (single-block and paired plain tiles) through thin tiles
+    try:
+        _check_rhf(lib, 5, 130, 90, 128 + 44, seed=43)
+        vv, vev = lib.moments_uhf(*args, 150)
+        assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL
+    finally:
+        lib.set_coulomb_factorization(2)
+
+
 def test_reference_drop_in_symbols(lib):
     """The void symbols with the reference's exact signature (optragf2.c:32-43, optuagf2.c:31-47)."""
     o, v, n, p = 6, 21, 50, 30

@@ -10,14 +10,15 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(0)
 sc = 1.0 / np.sqrt(n)
-ixq = torch.randn((o, p, n), generator=g, device=dev, dtype=torch.float64) * sc
-qja = torch.randn((n, o, v), generator=g, device=dev, dtype=torch.float64) * sc
+# (last dimensions padded to an even pitch: 16-byte TMA strides)
+ixq = torch.randn((o, p, n + (n & 1)), generator=g, device=dev, dtype=torch.float64) * sc
+qja = torch.randn((n, o, v + (v & 1)), generator=g, device=dev, dtype=torch.float64) * sc
 ei = torch.sort(torch.rand(o, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
 ea = torch.sort(torch.rand(v, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
 falg = 2.0 * p * o * o * v * n + 4.0 * p * p * o * o * v
 for r in range(reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    vv, vev = lib.moments_rhf_dev(ixq, qja, ei, ea, sync=True)
+    vv, vev = lib.moments_rhf_dev(ixq, qja, ei, ea, sync=True, naux=n)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     k1, k2, km, kc = lib.last_stage_ms()
     print("shape %s: %.4f s, %.2f TF/s alg | k1 %.2f ms (%.2f TF/s) k2 %.2f ms (%.2f TF/s alg) | M %.2f ms, coulomb %.2f ms | launches %d | checksum %.6e"
