@@ -323,14 +323,14 @@ def main():
     traffic = traffic_note = None
     try:   # DRAM bytes of one k1_form launch from the committed `ncu --set full` capture
         import csv
-        with open(os.path.join(ROOT, "profiles", "r01_k1_form_ncu.csv")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01c_k1_form_ncu.csv")) as f:
             rows = [r for r in csv.reader(f) if r and r[0] == "0"]
         m = {r[2]: (float(r[3]), r[4]) for r in rows}
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
         traffic = rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]]
         traffic_note = ("dram read+write bytes of one k1_form launch (grid %d) of tools/prof_case.py 64,100,4000,1100, "
-                        "profiles/r01_k1_form_ncu.csv; the path is tensor-bound, the figure only shows that (xi|ja) "
+                        "profiles/r01c_k1_form_ncu.csv; the path is tensor-bound, the figure only shows that (xi|ja) "
                         "is not spilled to HBM" % int(m["launch__grid_size"][0]))
     except Exception:
         pass

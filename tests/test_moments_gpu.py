@@ -240,3 +240,36 @@ def test_device_resident_async_and_sharded(lib):
     vv, vev = lib.moments_rhf_dev(ip, qp, T(ei, (o,)), T(ea, (v,)), naux=n)
     r = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o)
     assert relerr(vv.cpu().numpy(), r[0]) < TOL and relerr(vev.cpu().numpy(), r[1]) < TOL
+
+
+def test_edge_cases_and_errors(lib):
+    """Empty slice, single pole / single virtual, naux = 1, sharding into more parts than work items; argument errors
+    come back as status codes (Agf2B200Error), never as a crash or a silent CPU path."""
+    import torch
+    dev = torch.device("cuda", 0)
+    o, v, n, p = 6, 9, 20, 14
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 50)
+    vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p, 3, 3)            # empty slice: nothing accumulated
+    assert not vv.any() and not vev.any()
+    _check_rhf(lib, 1, 1, 1, 1, seed=51)
+    _check_rhf(lib, 1, 7, 5, 9, seed=52)                            # one pole: only the Coulomb-type term
+    _check_rhf(lib, 7, 1, 5, 9, seed=53)
+    _check_rhf(lib, 3, 5, 1, 140, seed=54)                          # naux = 1
+    T = lambda a, sh: torch.from_numpy(np.ascontiguousarray(a)).reshape(sh).to(dev)  # noqa: E731
+    # even pitch required by the device entry point: pad v = 9 -> 10
+    qp = torch.zeros((n, o, v + 1), dtype=torch.float64, device=dev); qp[:, :, :v] = T(qja, (n, o, v))
+    d = (T(ixq, (o, p, n)), qp, T(ei, (o,)), T(ea, (v,)))
+    acc = torch.zeros((2, p, p), dtype=torch.float64, device=dev)
+    for part in range(40):                                          # 40 parts > 21 pole pairs and > naux / 64 blocks
+        lib.moments_rhf_dev(*d, part=part, nparts=40, vv=acc[0], vev=acc[1])
+    r = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o)
+    a = acc.cpu().numpy()
+    assert relerr(a[0], r[0]) < TOL and relerr(a[1], r[1]) < TOL
+    with pytest.raises(lib.Agf2B200Error):
+        lib.moments_rhf(ixq, qja, ei, ea, p, 0, o, -1.0, 1.0)       # negative SCS factor
+    vv, vev = lib.moments_rhf(ixq, qja, ei, ea, p, 4, 2)            # istart > iend: the reference's loop runs zero times
+    assert not vv.any() and not vev.any()
+    with pytest.raises(lib.Agf2B200Error):
+        lib.moments_rhf_dev(*d, part=3, nparts=2)
+    with pytest.raises(lib.Agf2B200Error):
+        lib.moments_rhf_dev(T(ixq, (o, p, n)), T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))   # odd pitch (v = 9)

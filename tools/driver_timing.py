@@ -1,0 +1,28 @@
+"""Whole-driver timing: OptRAGF2 on a seeded model molecule of benzene cc-pVTZ size (BASELINE.json configs[1]:
+nphys=264, nocc=21, naux=700) for a few AGF2 iterations on the GPU; prints the per-phase wall times the reference
+records with @record_time (auxgf/util/decor.py:5-13) and the shapes of the sector calls."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from auxgf_b200.agf2 import OptRAGF2
+from auxgf_b200.hf import ModelRHF
+from auxgf_b200.lib import agf2 as lib
+
+nao, nocc, naux = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "264,21,700").split(",")]
+niter = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+t0 = time.perf_counter()
+hf = ModelRHF(nao=nao, nocc=nocc, naux=naux, seed=7).run()
+print("model RHF (host NumPy): %.1f s, E = %.10f" % (time.perf_counter() - t0, hf.e_tot))
+t0 = time.perf_counter()
+gf2 = OptRAGF2(hf, verbose=False, maxiter=niter)
+print("setup + MP2 build: %.2f s, E(mp2) = %.10f" % (time.perf_counter() - t0, gf2.e_mp2))
+lib.launch_count(reset=True)
+t0 = time.perf_counter()
+gf2.run()
+dt = time.perf_counter() - t0
+print("%d AGF2 iterations: %.2f s, E(tot) = %.10f, IP = %.6f, EA = %.6f, gf poles occ/vir = %d/%d"
+      % (gf2.iteration, dt, gf2.e_tot, gf2.ip[0], gf2.ea[0], gf2.gf.as_occupied().naux, gf2.gf.as_virtual().naux))
+print("phase timings (s):", {k: round(v, 3) for k, v in gf2._timings.items()})
+print("kernel launches:", lib.launch_count())
