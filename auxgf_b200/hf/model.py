@@ -33,10 +33,12 @@ def _model_integrals(nao, naux, seed, strength):
 
 
 def _jk(lpq, dm):
-    rho = np.einsum("Qpq,pq->Q", lpq, dm)
-    j = np.einsum("Q,Qpq->pq", rho, lpq)
-    tmp = np.einsum("Qpr,rs->Qps", lpq, dm)
-    k = np.einsum("Qps,Qqs->pq", tmp, lpq)
+    """J = sum_Q L_Q tr(L_Q D), K = sum_Q L_Q D L_Q as BLAS calls (L_Q symmetric)."""
+    naux, nao = lpq.shape[0], lpq.shape[1]
+    l2 = lpq.reshape(naux, nao * nao)
+    j = (l2.T @ (l2 @ dm.reshape(-1))).reshape(nao, nao)
+    tmp = np.matmul(lpq, dm)                                   # (Q, p, s) = L_Q D
+    k = tmp.transpose(1, 0, 2).reshape(nao, naux * nao) @ lpq.transpose(1, 0, 2).reshape(nao, naux * nao).T
     return j, k
 
 

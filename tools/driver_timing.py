@@ -13,7 +13,8 @@ from auxgf_b200.lib import agf2 as lib
 nao, nocc, naux = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "264,21,700").split(",")]
 niter = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 t0 = time.perf_counter()
-hf = ModelRHF(nao=nao, nocc=nocc, naux=naux, seed=7).run()
+# (weak coupling so that the plain fixed-point SCF of the model converges at this size)
+hf = ModelRHF(nao=nao, nocc=nocc, naux=naux, seed=7, strength=0.1).run(tol=1e-9, maxiter=150)
 print("model RHF (host NumPy): %.1f s, E = %.10f" % (time.perf_counter() - t0, hf.e_tot))
 t0 = time.perf_counter()
 gf2 = OptRAGF2(hf, verbose=False, maxiter=niter)
