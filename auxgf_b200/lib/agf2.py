@@ -295,6 +295,70 @@ def moments_uhf_dev(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, istart=0, iend=
     return vv, vev
 
 
+def moments_rhf_gathered(ixq, qja, ei, ea, nphys, os_factor=1.0, ss_factor=1.0):
+    """Host arrays in, host (vv, vev) out, on every rank of a torch.distributed (NCCL) job -- the multi-GPU
+    counterpart of ``moments_rhf``.  Instead of every rank pulling the whole of ``ixq``/``qja`` over PCIe (what the
+    reference's replicated MPI ranks imply, auxgf/mpi/agf2/optragf2.py:370-395), rank r uploads poles
+    [o r/W, o (r+1)/W) of ``ixq`` and rows [N r/W, N (r+1)/W) of ``qja``, the GPUs all-gather them over NVLink,
+    each builds its share of the pair-work items (part/nparts) and ONE all-reduce sums [vv|vev]."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ei = _c(ei, 1); ea = _c(ea, 1)
+    nocc, nvir = ei.size, ea.size
+    ixq = np.asarray(ixq).reshape(nocc, nphys, -1)
+    naux = ixq.shape[2]
+    qja = np.asarray(qja).reshape(naux, nocc, nvir)
+    ldn, ldv = naux + (naux & 1), nvir + (nvir & 1)              # even pitches (16-byte TMA strides)
+
+    def gather(host, n0, tail_shape, ld):
+        per = (n0 + world - 1) // world
+        full = torch.empty((world * per,) + tail_shape[:-1] + (ld,), dtype=torch.float64, device=dev)
+        lo, hi = min(n0, rank * per), min(n0, (rank + 1) * per)
+        mine = full[rank * per:(rank + 1) * per]
+        if ld != tail_shape[-1]:
+            mine.zero_()
+        if hi > lo:
+            mine[:hi - lo, ..., :tail_shape[-1]].copy_(torch.from_numpy(host[lo:hi]), non_blocking=False)
+        dist.all_gather_into_tensor(full, mine.clone() if world > 1 else mine)
+        return full[:n0]
+
+    d_ixq = gather(ixq, nocc, (nphys, naux), ldn)
+    d_qja = gather(qja, naux, (nocc, nvir), ldv)
+    d_ei = torch.from_numpy(ei).to(dev); d_ea = torch.from_numpy(ea).to(dev)
+    out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
+    moments_rhf_dev(d_ixq, d_qja, d_ei, d_ea, os_factor=os_factor, ss_factor=ss_factor, part=rank, nparts=world,
+                    vv=out[0], vev=out[1], sync=False, naux=naux)
+    dist.all_reduce(out)
+    h = out.cpu().numpy()
+    return h[0], h[1]
+
+
+def moments_rhf_multi(ixq, qja, ei, ea, nphys, os_factor=1.0, ss_factor=1.0):
+    """Host arrays in, host (vv, vev) out, summed over the ranks of a torch.distributed job (one process per GPU).
+    Two ways to get the inputs into HBM: (a) every rank streams the whole of ixq through the C host-pointer ABI, pole
+    by pole under its share of the pair loop -- free while the upload is shorter than the rank's compute; (b)
+    ``moments_rhf_gathered``: every rank uploads 1/world of the inputs and NVLink does the rest.  Picks (a) unless
+    the estimated upload (pageable host memory, ~8 GB/s) would outlast the rank's compute (~40 TFLOP/s)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    nocc, nvir = np.size(ei), np.size(ea)
+    naux = np.asarray(ixq).size // (nocc * nphys)
+    t_upload = 8.0 * nocc * nphys * naux / 8e9
+    t_compute = (2.0 * nphys * naux + 4.0 * nphys * nphys) * nocc * nocc * nvir / (40e12 * world)
+    if world > 1 and t_upload > 0.9 * t_compute:
+        return moments_rhf_gathered(ixq, qja, ei, ea, nphys, os_factor, ss_factor)
+    vv, vev = moments_rhf(ixq, qja, ei, ea, nphys, os_factor=os_factor, ss_factor=ss_factor, part=rank, nparts=world)
+    if world > 1:
+        buf = torch.from_numpy(np.stack([vv, vev])).cuda()
+        dist.all_reduce(buf)
+        vv, vev = buf.cpu().numpy()
+    return vv, vev
+
+
 def compress_dev(vv, vev):
     import torch
     n = vv.shape[0]

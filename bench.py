@@ -198,7 +198,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     def make(sh, scale, seed):
+        # the last dimension is padded to an even pitch (16-byte TMA strides); the logical extent is sh[-1]
         g = torch.Generator(device=dev); g.manual_seed(seed)
+        sh = tuple(sh[:-1]) + (sh[-1] + (sh[-1] & 1),)
         return torch.randn(sh, generator=g, device=dev, dtype=torch.float64) * scale
 
     sc = 1.0 / np.sqrt(n)
@@ -211,8 +213,8 @@ def main():
 
     def step():
         out.zero_()
-        lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, vv=out[0, 0], vev=out[0, 1], sync=False)
-        lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, vv=out[1, 0], vev=out[1, 1], sync=False)
+        lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, vv=out[0, 0], vev=out[0, 1], sync=False, naux=n)
+        lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, vv=out[1, 0], vev=out[1, 1], sync=False, naux=n)
         if world > 1:
             dist.all_reduce(out)
 
@@ -249,9 +251,9 @@ def main():
     # per-kernel device time of one more (untimed) step: per-launch CUDA events inside the library, with the
     # two-stream chunk overlap switched off so that each launch is timed alone on the GPU
     lib.set_overlap(False)
-    lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, sync=True)
+    lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, part=rank, nparts=world, sync=True, naux=n)
     st1, pl1 = lib.last_stage_ms(), lib.last_plan()
-    lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, sync=True)
+    lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, part=rank, nparts=world, sync=True, naux=n)
     st2, pl2 = lib.last_stage_ms(), lib.last_plan()
     lib.set_overlap(True)
     k1_ms, k2_ms, m_ms, c_ms = [a + b for a, b in zip(st1, st2)]
@@ -263,7 +265,7 @@ def main():
     # ------------------------------------------------------------------ e2e (host buffers, every rank)
     e2e = None
     if not args.no_e2e:
-        host_gb = (ixq_o.numel() + qja_o.numel() + ixq_v.numel() + qja_v.numel()) * 8 / 1e9
+        host_gb = ((o + v) * p * n + 2 * n * o * v) * 8 / 1e9
         try:
             avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 1e9
         except Exception:
@@ -273,8 +275,10 @@ def main():
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if ok.item() > 0:
-            h = [ixq_o.cpu().numpy().reshape(o * p, n), qja_o.cpu().numpy().reshape(n, o * v),
-                 ixq_v.cpu().numpy().reshape(v * p, n), qja_v.cpu().numpy().reshape(n, v * o)]
+            h = [np.ascontiguousarray(ixq_o[:, :, :n].cpu().numpy()).reshape(o * p, n),
+                 np.ascontiguousarray(qja_o[:, :, :v].cpu().numpy()).reshape(n, o * v),
+                 np.ascontiguousarray(ixq_v[:, :, :n].cpu().numpy()).reshape(v * p, n),
+                 np.ascontiguousarray(qja_v[:, :, :o].cpu().numpy()).reshape(n, v * o)]
             eo_h, ev_h = e_o.cpu().numpy(), e_v.cpu().numpy()
             del ixq_o, qja_o, ixq_v, qja_v
             torch.cuda.empty_cache()
@@ -282,14 +286,12 @@ def main():
             def host_step():
                 # the call a user of the reference makes: host DF blocks in, host vv/vev out (per rank: its share
                 # of the pair-work items), then the one all-reduce of [vv|vev] over the ranks
-                r0 = lib.moments_rhf(h[0], h[1], eo_h, ev_h, p, part=rank, nparts=world)
-                r1 = lib.moments_rhf(h[2], h[3], ev_h, eo_h, p, part=rank, nparts=world)
-                res = np.stack([r0[0], r0[1], r1[0], r1[1]]).reshape(2, 2, p, p)
-                if world > 1:
-                    buf = torch.from_numpy(res).to(dev)
-                    dist.all_reduce(buf)
-                    res = buf.cpu().numpy()
-                return res
+                # C host-pointer ABI (ixq streams in pole by pole under the pair loop) on every rank, or -- when
+                # that upload would outlast a rank's compute (N = 8 at the S shape) -- 1/N of the inputs per rank +
+                # NCCL all-gather over NVLink; one all-reduce of [vv|vev] either way
+                r0 = lib.moments_rhf_multi(h[0], h[1], eo_h, ev_h, p)
+                r1 = lib.moments_rhf_multi(h[2], h[3], ev_h, eo_h, p)
+                return np.stack([r0[0], r0[1], r1[0], r1[1]]).reshape(2, 2, p, p)
             host_step()
             n_e2e = max(1, min(args.steps, 2))
             sync_all()
@@ -304,13 +306,15 @@ def main():
             chk2 = float(res.sum())
             dev_vs_host = max(float(np.abs(res[k, m] - out_host[k, m]).max() / np.abs(out_host[k, m]).max())
                               for k in range(2) for m in range(2))
-            red = 4 * p * p * 8 if world > 1 else 0
-            e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v) + red,
-                   "d2h_bytes_per_step": 4 * p * p * 8 + red, "bytes_are": "per rank", "tflops": flops_build / dt * 1e-12,
+            e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(host_gb * 1e9) + 8 * 2 * (o + v),
+                   "h2d_note": "upper bound per rank: ranks that take the all-gather route upload 1/N of it",
+                   "d2h_bytes_per_step": 4 * p * p * 8, "bytes_are": "per rank", "tflops": flops_build / dt * 1e-12,
                    "checksum_rel_diff_vs_device_path": abs(chk2 - checksum) / max(abs(checksum), 1e-300),
                    "max_rel_diff_vs_device_path": dev_vs_host,
-                   "api": "agf2_b200_build_part_loop_rhf_sharded (host pointers, pageable NumPy buffers; "
-                          "ixq upload pipelined under the pair loop)"}
+                   "api": "auxgf_b200.lib.agf2.moments_rhf_multi: agf2_b200_build_part_loop_rhf_sharded (host pointers, "
+                          "pageable NumPy buffers, ixq upload pipelined under the pair loop) or, when the upload would "
+                          "outlast a rank's compute, 1/N upload + NCCL all-gather + agf2_b200_moments_rhf_dev; one "
+                          "all-reduce of [vv|vev]"}
         else:
             e2e = {"value": None, "unit": "s", "skipped": "host RAM %.0f GB < %.0f GB needed for the host copies" % (avail_gb, need_gb)}
 
