@@ -16,14 +16,31 @@ def diag_fock_ext(se, fock, nelec, chempot=0.0, occupancy=2.0, buf=None):
     return w, v, chempot_phys, error
 
 
-def objective(x, se, fock, nelec, occupancy=2.0, buf=None):
-    x = float(np.ravel(x)[0])
-    return diag_fock_ext(se, fock, nelec, chempot=x, occupancy=occupancy, buf=buf)[3] ** 2
+class _LastSolve:
+    """SciPy asks for the objective and for its gradient at the same point in two separate calls (so does the
+    reference, chempot.py:187-190: two eigensolves per point); remember the last eigensolve and reuse it."""
+
+    def __init__(self):
+        self.x = None
+        self.result = None
+
+    def __call__(self, x, se, fock, nelec, occupancy, buf):
+        if self.x != x:
+            self.result = diag_fock_ext(se, fock, nelec, chempot=x, occupancy=occupancy, buf=buf)
+            self.x = x
+        return self.result
 
 
-def gradient(x, se, fock, nelec, occupancy=2.0, buf=None, return_val=False):
+def objective(x, se, fock, nelec, occupancy=2.0, buf=None, memo=None):
     x = float(np.ravel(x)[0])
-    w, v, chempot, error = diag_fock_ext(se, fock, nelec, chempot=x, occupancy=occupancy, buf=buf)
+    solve = memo if memo is not None else _LastSolve()
+    return solve(x, se, fock, nelec, occupancy, buf)[3] ** 2
+
+
+def gradient(x, se, fock, nelec, occupancy=2.0, buf=None, return_val=False, memo=None):
+    x = float(np.ravel(x)[0])
+    solve = memo if memo is not None else _LastSolve()
+    w, v, chempot, error = solve(x, se, fock, nelec, occupancy, buf)
     nocc = int(np.sum(w < chempot))
     n = se.nphys
     h_1 = -(v[n:, nocc:].T @ v[n:, :nocc])
@@ -37,11 +54,12 @@ def gradient(x, se, fock, nelec, occupancy=2.0, buf=None, return_val=False):
 def minimize(se, fock, nelec, occupancy=2.0, buf=None, x0=0.0, tol=1e-6, maxiter=200, jac=True):
     """Shifts ``se`` in place (energies -= x, chempot updated) and returns (se, opt)."""
     tol2 = tol ** 2
-    args = (se, fock, nelec, occupancy, buf)
+    memo = _LastSolve()
+    args = (se, fock, nelec, occupancy, buf, memo)
     kwargs = dict(x0=np.array([x0]), method="TNC", bounds=[(None, None)],
                   options=dict(maxfun=maxiter, ftol=tol2, xtol=tol2, gtol=tol2))
     if jac:
-        kwargs["jac"] = lambda *a: np.array([gradient(*a)])
+        kwargs["jac"] = lambda x, *a: np.array([gradient(x, *a[:5], memo=a[5])])
     opt = optimize.minimize(objective, args=args, **kwargs)
     se._ener -= float(np.ravel(opt.x)[0])
     se.chempot = find_chempot(se.nphys, nelec, se.eig(fock), occupancy=occupancy)[0]

@@ -19,6 +19,24 @@ print("model RHF (host NumPy): %.1f s, E = %.10f" % (time.perf_counter() - t0, h
 t0 = time.perf_counter()
 gf2 = OptRAGF2(hf, verbose=False, maxiter=niter)
 print("setup + MP2 build: %.2f s, E(mp2) = %.10f" % (time.perf_counter() - t0, gf2.e_mp2))
+# count / time the two device services the Fock loop leans on (dense eigensolve, DF-JK)
+stats = {"eigh": [0, 0.0, 0], "get_jk": [0, 0.0, 0]}
+_eigh, _jk = lib.eigh, lib.DeviceERI.get_jk
+
+
+def eigh_timed(a):
+    t = time.perf_counter(); r = _eigh(a); stats["eigh"][0] += 1; stats["eigh"][1] += time.perf_counter() - t
+    stats["eigh"][2] = max(stats["eigh"][2], a.shape[0])
+    return r
+
+
+def jk_timed(self, rdm1):
+    t = time.perf_counter(); r = _jk(self, rdm1); stats["get_jk"][0] += 1; stats["get_jk"][1] += time.perf_counter() - t
+    return r
+
+
+lib.eigh = eigh_timed
+lib.DeviceERI.get_jk = jk_timed
 lib.launch_count(reset=True)
 t0 = time.perf_counter()
 gf2.run()
@@ -27,3 +45,5 @@ print("%d AGF2 iterations: %.2f s, E(tot) = %.10f, IP = %.6f, EA = %.6f, gf pole
       % (gf2.iteration, dt, gf2.e_tot, gf2.ip[0], gf2.ea[0], gf2.gf.as_occupied().naux, gf2.gf.as_virtual().naux))
 print("phase timings (s):", {k: round(v, 3) for k, v in gf2._timings.items()})
 print("kernel launches:", lib.launch_count())
+print("eigh: %d calls, %.2f s total (largest n = %d); get_jk: %d calls, %.2f s total"
+      % (stats["eigh"][0], stats["eigh"][1], stats["eigh"][2], stats["get_jk"][0], stats["get_jk"][1]))
