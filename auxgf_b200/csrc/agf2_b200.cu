@@ -355,7 +355,7 @@ int run_coulomb(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
         if (int r = launch_k2(L, st)) return r;
     }
     if (msym) {
-        dim3 gm((unsigned)((naux + 127) / 128), (unsigned)naux);
+        dim3 gm((unsigned)naux, (unsigned)((naux + 127) / 128));
         mirror_m<<<gm, 128, 0, st>>>(c.Mbuf, (int)naux, nq_pad, ldm);
         CU_TRY(cudaGetLastError());
         c.launches++;

@@ -721,7 +721,7 @@ __global__ void fill_m_weights(double* __restrict__ w0, double* __restrict__ w1,
 // M = [M0 | M1] (n rows, two n_pad-wide halves, pitch ld) was accumulated on its upper triangle: fill the lower one
 __global__ void mirror_m(double* __restrict__ m, int n, long long n_pad, long long ld)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x, r = blockIdx.x;   // rows on grid.x: naux may exceed 65535
     if (c < r && c < n) {
         m[(long long)r * ld + c] = m[(long long)c * ld + r];
         m[(long long)r * ld + n_pad + c] = m[(long long)c * ld + n_pad + r];
