@@ -25,6 +25,7 @@ from auxgf_b200.util import Timer, find_chempot, record_energy, record_time
 _DEFAULTS = {
     "maxiter": 50, "etol": 1e-6, "wtol": 1e-12, "damping": 0.0, "delay_damping": 0, "dtol": 1e-8,
     "diis_space": 8, "fock_maxiter": 50, "fock_maxruns": 20, "maxblk": 120, "ss_factor": 1.0, "os_factor": 1.0,
+    "checkpoint": False,      # rank 0 writes rdm1_chk.dat / se_chk.pickle every iteration (mpi/agf2/optragf2.py:35,568-570)
 }
 
 
@@ -233,10 +234,16 @@ class OptRAGF2:
                 if e_dif < etol and self.converged:
                     break
                 self.converged = e_dif < etol
+            if self.options["checkpoint"] and dist_info()[0] == 0:
+                self._write_checkpoint()
         self._log("Auxiliary GF2 %s after %d iterations." % ("converged" if self.converged else "failed to converge",
                                                             self.iteration))
         self._timings["total"] = self._timings.get("total", 0.0) + self._timer.total()
         return self
+
+    def _write_checkpoint(self):
+        np.savetxt("rdm1_chk.dat", self.rdm1)
+        self.se.save("se_chk.pickle")
 
     # ---------------------------------------------------------------------------------------------
     @property

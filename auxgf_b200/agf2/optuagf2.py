@@ -92,6 +92,13 @@ class OptUAGF2(OptRAGF2):
         self._log("E(mp2) = %.12f" % emp2)
         return emp2
 
+    def _write_checkpoint(self):
+        """mpi/agf2/optuagf2.py:479-483"""
+        np.savetxt("rdm1_alph_chk.dat", self.rdm1[0])
+        np.savetxt("rdm1_beta_chk.dat", self.rdm1[1])
+        self.se[0].save("se_alph_chk.pickle")
+        self.se[1].save("se_beta_chk.pickle")
+
     @property
     def chempot(self):
         return tuple(s.chempot for s in self.se)

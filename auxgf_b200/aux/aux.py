@@ -89,6 +89,40 @@ class Aux:
         h_ext = self.as_hamiltonian(h_phys, chempot=chempot, out=out)
         return backend.get().eigh(h_ext)
 
+    def dot(self, h_phys, vec, chempot=0.0):
+        """``as_hamiltonian(h_phys, chempot) @ vec`` without building the extended matrix (aux.py:420-465)."""
+        h_phys = np.asarray(h_phys)
+        n = self.nphys
+        if h_phys.shape != (n, n):
+            raise ValueError("physical space of h_phys and couplings must match.")
+        vec = np.asarray(vec)
+        shape = vec.shape
+        vec = vec.reshape(n + self.naux, -1)
+        out = np.empty(vec.shape, dtype=np.result_type(self.v.dtype, vec.dtype))
+        out[:n] = h_phys @ vec[:n] + self.v @ vec[n:]
+        out[n:] = self.v.T @ vec[:n] + (self.e[:, None] - chempot) * vec[n:]
+        return out.reshape(shape)
+
+    def memsize(self):
+        """Approximate size in GB (aux.py:764-775)."""
+        return (self.e.nbytes + self.v.nbytes + 8) / 1e9
+
+    def __eq__(self, other):
+        """Same spectrum: the reference compares spectral functions on an imaginary-frequency grid (aux.py:849-868,
+        ImFqGrid(32, beta=8), Feynman ordering); restated here as  v (i w_n - e)^-1 v^T  on those Matsubara points."""
+        if not isinstance(other, Aux):
+            return NotImplemented
+        if self.nphys != other.nphys:
+            return False
+        wn = (2 * np.arange(32) + 1) * np.pi / 8.0
+
+        def spectrum(a):
+            d = 1.0 / (1j * wn[:, None] - (a.e - a.chempot)[None, :])
+            return np.einsum("xk,wk,yk->wxy", a.v, d, a.v)
+        return bool(np.allclose(spectrum(self), spectrum(other)))
+
+    __hash__ = None
+
     def moment(self, n):
         n = np.asarray(n, dtype=np.int64).reshape(-1)
         moms = np.stack([(self.v * self.e[None] ** k) @ self.v.T for k in n])
@@ -122,6 +156,14 @@ class Aux:
     @property
     def w(self):
         return np.einsum("xk,xk->k", self.v, self.v)
+
+    @property
+    def w_occ(self):
+        return np.einsum("xk,xk->k", self.v_occ, self.v_occ)
+
+    @property
+    def w_vir(self):
+        return np.einsum("xk,xk->k", self.v_vir, self.v_vir)
 
     @property
     def nphys(self):

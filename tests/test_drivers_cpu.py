@@ -47,6 +47,33 @@ def test_aux_container():
         a.as_hamiltonian(np.eye(4))
 
 
+def test_aux_dot_eq_and_io(tmp_path):
+    rng = np.random.default_rng(3)
+    e = np.sort(rng.standard_normal(6)); v = rng.standard_normal((4, 6))
+    a = Aux(e, v, chempot=-0.2)
+    h = rng.standard_normal((4, 4)); h = h + h.T
+    x = rng.standard_normal((10, 3))
+    assert np.allclose(a.dot(h, x, chempot=0.4), a.as_hamiltonian(h, chempot=0.4) @ x)
+    assert np.allclose(a.dot(h, x[:, 0]), a.as_hamiltonian(h) @ x[:, 0])
+    perm = rng.permutation(6)
+    assert a == Aux(e[perm], v[:, perm], chempot=-0.2)          # same spectrum, poles in another order
+    assert not (a == Aux(e + 0.05, v, chempot=-0.2))
+    assert np.allclose(a.w_occ.sum() + a.w_vir.sum(), a.w.sum()) and a.memsize() > 0
+    a.save(str(tmp_path / "se.pickle"))
+    b = Aux.load(str(tmp_path / "se.pickle"))
+    assert b == a and b.chempot == a.chempot
+
+
+def test_checkpoint_option(oracle_backend, tmp_path, monkeypatch):
+    """`checkpoint=True` (mpi/agf2/optragf2.py:35,568-570): rank 0 writes the density matrix and the self-energy."""
+    from auxgf_b200.agf2 import OptRAGF2
+    monkeypatch.chdir(tmp_path)
+    hf = ModelRHF(nao=6, nocc=2, naux=10, seed=0).run()
+    gf2 = OptRAGF2(hf, verbose=False, maxiter=2, checkpoint=True).run()
+    assert np.allclose(np.loadtxt("rdm1_chk.dat"), gf2.rdm1)
+    assert Aux.load("se_chk.pickle") == gf2.se
+
+
 def test_unknown_option_rejected(oracle_backend):
     from auxgf_b200.agf2 import OptRAGF2
     hf = ModelRHF(nao=6, nocc=2, naux=10, seed=0).run()
