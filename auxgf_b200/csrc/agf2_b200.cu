@@ -1,14 +1,7 @@
 // libagf2_b200.so -- host side of the B200 moment build: work planner, TMA descriptors, launches,
 // and the C-ABI of include/agf2_b200.h.  Reference paths are relative to obackhouse/auxgf.
 //
-// Plan (replaces the `for i` loop of auxgf/lib/libagf2/optragf2.c:118 and its MPI split in
-// auxgf/mpi/agf2/optragf2.py:370-374):
-//   work items   DIAG(i)      X_ii                -> one column block  sqrt(os) X_ii
-//                PAIR(i>j)    X_ij, X_ji          -> two column blocks sqrt(os/2+ss)(X_ij-X_ji), sqrt(os/2)(X_ij+X_ji)
-//                OS(i,J)      X_iJ (other spin)   -> one column block  sqrt(os) X_iJ           (UHF only)
-//                ASYM(i,j)    j outside [istart,iend): U = X_ij -> W0, V = (c X_ij - s X_ji) -> W1
-//   items are dealt round-robin to `nparts` (one per GPU); each part packs its items into chunks whose
-//   column blocks fit the L2-sized workspace; per chunk: k1_form (integrals -> W), k2_moment (W -> vv, vev).
+// The work planner lives in planner.h (pure host code); this file executes its chunks.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cublas_v2.h>
@@ -25,6 +18,7 @@
 
 #include "../../include/agf2_b200.h"
 #include "moment_kernels.cuh"
+#include "planner.h"
 
 using namespace agf2;
 
@@ -52,6 +46,7 @@ struct EventPair { cudaEvent_t a, b; int kind; };
 
 struct Ctx {
     bool init = false;
+    bool env_applied = false;
     int device = -1;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -108,6 +103,22 @@ struct Ctx {
 };
 Ctx g_ctx;
 
+// Environment overrides of the planner / scheduling knobs (read once; no CUDA needed).
+void apply_env() {
+    Ctx& c = g_ctx;
+    if (c.env_applied) return;
+    c.env_applied = true;
+    if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
+    if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_LPT")) c.lpt_order = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_BALANCED")) c.balanced_blocks = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_TUNE_CHUNK")) c.tune_chunk = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_COULOMB")) { c.coulomb = atoi(e) != 0; c.coulomb_auto = atoi(e) == 2; }
+    if (const char* e = getenv("AGF2_B200_K2_MASK")) c.k2_mask = atoi(e) != 0;
+    if (const char* e = getenv("AGF2_B200_THIN")) c.thin_tiles = atoi(e) != 0;
+}
+
 int ensure_ctx() {
     Ctx& c = g_ctx;
     if (c.init) return 0;
@@ -141,15 +152,7 @@ int ensure_ctx() {
     CU_TRY(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
     CU_TRY(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-    if (const char* e = getenv("AGF2_B200_OVERLAP")) c.overlap = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_WORKSPACE_MB")) c.ws_bytes = (int64_t)atoll(e) << 20;
-    if (const char* e = getenv("AGF2_B200_SIMPLE")) c.simple = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_LPT")) c.lpt_order = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_BALANCED")) c.balanced_blocks = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_TUNE_CHUNK")) c.tune_chunk = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_COULOMB")) { c.coulomb = atoi(e) != 0; c.coulomb_auto = atoi(e) == 2; }
-    if (const char* e = getenv("AGF2_B200_K2_MASK")) c.k2_mask = atoi(e) != 0;
-    if (const char* e = getenv("AGF2_B200_THIN")) c.thin_tiles = atoi(e) != 0;
+    apply_env();
     if (cublasCreate(&c.blas) != CUBLAS_STATUS_SUCCESS) return fail(AGF2_B200_ESOLVER, "cublasCreate failed");
     c.init = true;
     return 0;
@@ -185,11 +188,6 @@ struct Spin {            // one (Q|ja) tensor and its energies
     const double* ei_dev = nullptr;
 };
 
-struct Item { int kind, i, j; };   // kind: 0 DIAG, 1 PAIR, 2 OS, 3 ASYM
-struct SubTile { int i, j, a0, nb, bsel, esel, nv; long long col; double p, eij; };
-
-inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
-
 // Host-pointer API only: ixq is uploaded pole by pole on a copy stream by a helper thread while the GPU
 // already works on the pairs whose poles have landed.  rank[i] = position of pole i in the upload order,
 // ev[k] is recorded after the k-th upload, ready = number of uploads whose event has been recorded.
@@ -218,54 +216,6 @@ void record(cudaStream_t st, int kind, bool begin) {
     }
 }
 
-// Column blocks (a0, nb) of one item of padded width w: ceil(w/64) blocks of nearly equal width (in units of
-// 8 columns), e.g. 104 -> 56 + 48 rather than 64 + 40, so that the CTA tiles of a launch have similar durations.
-std::vector<std::pair<int, int>> split_blocks(int64_t w, bool balanced) {
-    std::vector<std::pair<int, int>> out;
-    const int units = (int)(w / 8);
-    const int nblk = (units + 7) / 8;
-    int a0 = 0;
-    for (int b = 0; b < nblk; ++b) {
-        int nb = balanced ? units / nblk + (b < units % nblk ? 1 : 0) : std::min(8, units - 8 * b);
-        out.push_back({a0, nb});
-        a0 += 8 * nb;
-    }
-    return out;
-}
-
-// Greedy in-order dispatch of CTA tiles (durations in units of one 8-column block) over nsm SMs: the time the
-// last SM finishes.  This is how the hardware block scheduler hands out the CTAs of one k1_form launch.
-double dispatch_makespan(const std::vector<double>& durs, int nsm) {
-    std::vector<double> h((size_t)nsm, 0.0);   // min-heap of SM finish times
-    auto cmp = [](double a, double b) { return a > b; };
-    for (double d : durs) {
-        std::pop_heap(h.begin(), h.end(), cmp);
-        h.back() += d;
-        std::push_heap(h.begin(), h.end(), cmp);
-    }
-    return *std::max_element(h.begin(), h.end());
-}
-
-// How many identical work items one chunk should hold (<= n_max, what the workspace allows) so that the tiles
-// of the k1_form launch fill an integer number of waves: maximises work / (makespan + launch overhead).
-int pick_chunk_items(const std::vector<double>& item_tiles, int n_max, int nsm, bool lpt, double launch_ovh) {
-    if (n_max <= 1) return 1;
-    int best_n = n_max;
-    double best = -1.0;
-    const int lo = std::max(1, n_max / 2), step = std::max(1, (n_max - lo) / 48);
-    double per_item = 0.0;
-    for (double d : item_tiles) per_item += d;
-    for (int n = n_max; n >= lo; n -= step) {
-        std::vector<double> durs;
-        durs.reserve(item_tiles.size() * (size_t)n);
-        for (int k = 0; k < n; ++k) durs.insert(durs.end(), item_tiles.begin(), item_tiles.end());
-        if (lpt) std::stable_sort(durs.begin(), durs.end(), [](double a, double b) { return a > b; });
-        const double eff = per_item * n / nsm / (dispatch_makespan(durs, nsm) + launch_ovh);
-        if (eff > best * 1.005) { best = eff; best_n = n; }   // prefer the larger chunk unless clearly worse
-    }
-    return best_n;
-}
-
 struct K2Launch {
     CUtensorMap a0, a1, b;
     K2Params p;
@@ -284,6 +234,15 @@ int launch_k2(const K2Launch& L, cudaStream_t st) {
     CU_TRY(cudaGetLastError());
     c.launches++;
     return 0;
+}
+
+PlanConfig plan_config() {
+    const Ctx& c = g_ctx;
+    PlanConfig p;
+    p.ws_bytes = c.ws_bytes; p.num_sms = c.num_sms; p.simple = c.simple; p.lpt_order = c.lpt_order;
+    p.balanced_blocks = c.balanced_blocks; p.tune_chunk = c.tune_chunk; p.thin_tiles = c.thin_tiles;
+    p.coulomb = c.coulomb; p.coulomb_auto = c.coulomb_auto;
+    return p;
 }
 
 // Coulomb part of the moments without forming a single Coulomb integral:
@@ -416,53 +375,22 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
 {
     Ctx& c = g_ctx;
     const int64_t o = same.nocc, v = same.nvir;
-    if (nphys <= 0 || naux <= 0 || o <= 0 || v <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
-    if (istart < 0 || iend > o || istart > iend) return fail(AGF2_B200_EINVAL, "bad [istart, iend)");
-    if (nparts < 1 || part < 0 || part >= nparts) return fail(AGF2_B200_EINVAL, "bad part/nparts");
-    if (c_same - s_same < 0 || c_same + s_same < 0 || os_other < 0)
-        return fail(AGF2_B200_EINVAL, "os_factor and ss_factor must be non-negative");
+    MomentPlan plan;
+    if (int r = plan.init(plan_config(), nphys, naux, o, v, other != nullptr, other ? other->nocc : 0,
+                          other ? other->nvir : 0, istart, iend, c_same, s_same, os_other, part, nparts))
+        return fail(r, plan.error);
     if ((ld_ixq & 1) || ld_ixq < naux || (same.ld & 1) || same.ld < v || (other && ((other->ld & 1) || other->ld < other->nvir)))
         return fail(AGF2_B200_EINVAL, "leading dimensions must be even (16-byte TMA strides) and >= the row length");
     if ((reinterpret_cast<uintptr_t>(ixq) & 15) || (reinterpret_cast<uintptr_t>(same.qja) & 15) ||
         (other && (reinterpret_cast<uintptr_t>(other->qja) & 15)))
         return fail(AGF2_B200_EINVAL, "device arrays must be 16-byte aligned");
-    if (nphys > (1 << 30) || naux > (1 << 30) || o * v > (1ll << 40) || o > 65535 || (other && other->nocc > 65535))
-        return fail(AGF2_B200_EINVAL, "dimension too large");
-
-    const int64_t p_pad = rup(nphys, kTileM);
-    const int nxb = (int)(p_pad / kTileM);
-    const int nyb = (int)((nphys + kTileN - 1) / kTileN);
-    const int64_t vpad = rup(v, 8);
-    const int64_t vbpad = other ? rup(other->nvir, 8) : 0;
-    // Coulomb factorisation (default): the pair loop only carries the exchange-type term  s sum_{i>j} A A^T,
-    // A = X_ij - X_ji; every Coulomb-type term goes through run_coulomb.  Otherwise (debug / simple kernels):
-    // pairs carry sqrt(c/2+s/2) A and sqrt(c/2-s/2) S, plus DIAG and OS items.
-    bool fact = c.coulomb && !c.simple;
-    if (fact && c.coulomb_auto) {
-        // flops the factorisation removes from the pair loop (S blocks, DIAG and OS items) vs the flops it adds
-        const double P = (double)nphys, N = (double)naux, ni = (double)(iend - istart), tri = 0.61;
-        const double no = (double)o, ov = no * (double)v;
-        const double obvb = other ? (double)other->nocc * (double)other->nvir : 0.0;
-        const double k2col = 2.0 * tri * 2.0 * P * P;                       // both moments, per workspace column
-        double direct = 0.5 * ni * (ni - 1.0) * v * k2col * (c_same != s_same ? 1.0 : 0.0);   // S blocks
-        direct += (c_same != s_same ? ni * ((double)v * k2col + 2.0 * P * v * N) : 0.0);         // DIAG items
-        direct += os_other != 0.0 ? ni * (obvb * k2col + 2.0 * P * obvb * N) : 0.0;             // OS items
-        const bool partial_slice = istart > 0 || iend < o;
-        double mcols = 0.0;                                                  // (j, a) columns of the M build
-        if (c_same != s_same || (partial_slice && c_same != 0.0)) mcols += ov;
-        if (os_other != 0.0) mcols += obvb;
-        const double fwork = (nparts == 1 ? 0.5 : 1.0) * 4.0 * N * N * mcols + ni * (4.0 * P * N * N + k2col * N);
-        fact = mcols > 0.0 && fwork < 0.95 * direct;
-    }
-    const double ca = fact ? std::sqrt(s_same) : std::sqrt(0.5 * (c_same + s_same));
-    const double cs = fact ? 0.0 : std::sqrt(0.5 * (c_same - s_same));
-    const double cd = fact ? 0.0 : std::sqrt(c_same - s_same), co = fact ? 0.0 : std::sqrt(os_other);
-    const double asym_c = fact ? 0.0 : c_same;
-    const bool want_asym = !(fact && s_same == 0.0);
+    const int64_t p_pad = plan.p_pad, cap_cols = plan.cap_cols;
+    const int nxb = plan.nxb, nyb = plan.nyb;
+    const bool fact = plan.fact;
+    const std::vector<Item>& sym_items = plan.sym_items;
+    const std::vector<Item>& asym_items = plan.asym_items;
 
     // ---- scratch ------------------------------------------------------------------------------
-    int64_t cap_cols = std::max<int64_t>(c.ws_bytes / (p_pad * 8), 2 * std::max(vpad, vbpad));
-    cap_cols = rup(cap_cols, 16);
     const size_t w_need = (size_t)p_pad * cap_cols;
     if (w_need > c.w_elems) {
         CU_TRY(cudaDeviceSynchronize());
@@ -516,82 +444,11 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     }
     const int nk1 = (int)((naux + kKB - 1) / kKB);
 
-    // ---- items of this part -----------------------------------------------------------------------
-    // (kinds are kept contiguous -- PAIR, then DIAG, then OS -- so that the chunks are homogeneous and their
-    // size can be tuned to whole waves of CTA tiles; within a kind the order is i-major, which is also the
-    // order in which the host-pointer API uploads the poles)
-    std::vector<Item> sym_items, asym_items;
-    {
-        int64_t n_diag = 0, n_pair = 0, n_os = 0, n_asym = 0;
-        std::vector<Item> diag_items, os_items;
-        for (int64_t i = istart; i < iend; ++i) {
-            if (cd != 0.0 && (n_diag++ % nparts) == part) diag_items.push_back({0, (int)i, (int)i});
-            if (ca != 0.0 || cs != 0.0)
-                for (int64_t j = istart; j < i; ++j)
-                    if ((n_pair++ % nparts) == part) sym_items.push_back({1, (int)i, (int)j});
-            if (other && co != 0.0)
-                for (int64_t J = 0; J < other->nocc; ++J)
-                    if ((n_os++ % nparts) == part) os_items.push_back({2, (int)i, (int)J});
-            if (want_asym)
-                for (int64_t j = 0; j < o; ++j)
-                    if ((j < istart || j >= iend) && (n_asym++ % nparts) == part) asym_items.push_back({3, (int)i, (int)j});
-        }
-        sym_items.insert(sym_items.end(), diag_items.begin(), diag_items.end());
-        sym_items.insert(sym_items.end(), os_items.begin(), os_items.end());
-    }
     c.last_plan[0] = fact ? 1 : 0;
     c.last_plan[1] = c.last_plan[2] = c.last_plan[3] = 0;
     for (const Item& it : sym_items) c.last_plan[it.kind == 1 ? 1 : (it.kind == 0 ? 2 : 3)]++;
     c.last_plan[4] = (int64_t)asym_items.size();
     c.last_plan[5] = 0;
-    const std::vector<std::pair<int, int>> blk_same = split_blocks(vpad, c.balanced_blocks);
-    const std::vector<std::pair<int, int>> blk_other = split_blocks(vbpad, c.balanced_blocks);
-    // thin-tile mapping of the last x-block (k1_mainloop_thin): number of valid 8-row blocks, 0 = full tile
-    auto thin_mbv = [&](int xb, int nb1, int nb2) -> int {
-        if (!c.thin_tiles || c.simple || xb != nxb - 1) return 0;
-        const int mbv = (int)((nphys - (int64_t)xb * kTileM + 7) / 8);
-        if (mbv > 10) return 0;
-        const int nsets = (nb1 > 0) + (nb2 > 0);
-        return (1.15 * mbv * nsets < 2.0 * (nb1 + nb2)) ? mbv : 0;   // per-warp DMMA count: thin vs full
-    };
-    auto tile_work = [](const K1Tile& t) -> int {   // per-warp DMMAs per k-step (x 2): the tile's duration
-        return t.mbv > 0 ? t.mbv * ((t.nb1 > 0) + (t.nb2 > 0)) : 2 * (t.nb1 + t.nb2);
-    };
-    // items per chunk, per kind (0 = not yet chosen)
-    int chunk_items[4] = {0, 0, 0, 0};
-    auto items_per_chunk = [&](int kind) -> int {
-        if (chunk_items[kind]) return chunk_items[kind];
-        const int64_t w = kind == 2 ? vbpad : vpad;
-        const int nblk = kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
-        const int n_max = (int)std::max<int64_t>(1, cap_cols / std::max<int64_t>(1, nblk * w));
-        int n = n_max;
-        if (c.tune_chunk && !c.simple) {
-            // tile durations of one item, in 8-column units; ~0.15 units of fill + epilogue per tile at nk = 250
-            const double ovh = 0.15 * 250.0 / std::max(1, (int)((naux + kKB - 1) / kKB));
-            std::vector<double> t;
-            const auto& blks = kind == 2 ? blk_other : blk_same;
-            if (kind == 1 || kind == 3) {
-                for (int xb = 0; xb < nxb; ++xb)
-                    for (auto& b : blks) {
-                        const int mbv = thin_mbv(xb, b.second, b.second);
-                        t.push_back((mbv ? (double)mbv : 2.0 * b.second) + ovh);
-                    }
-            } else {
-                // plain blocks pair up two by two across items: model one item as half-tiles
-                for (int xb = 0; xb < nxb; ++xb)
-                    for (auto& b : blks) {
-                        const int mbv = thin_mbv(xb, b.second, b.second);
-                        t.push_back((mbv ? 0.5 * mbv : (double)b.second) + 0.5 * ovh);
-                    }
-            }
-            n = pick_chunk_items(t, n_max, c.num_sms, c.lpt_order, 0.5);
-        }
-        chunk_items[kind] = n;
-        if (getenv("AGF2_B200_VERBOSE"))
-            fprintf(stderr, "agf2_b200: kind %d: %d items per chunk (workspace allows %d), %d column blocks/item\n", kind, n,
-                    n_max, (int)(kind == 2 ? blk_other : blk_same).size());
-        return n;
-    };
 
     // K2 tile lists (upper-triangle for symmetric chunks, all tiles for non-symmetric ones)
     std::vector<K2Tile> t2_sym, t2_all;
@@ -615,95 +472,15 @@ int run_moments(const double* ixq, int64_t ld_ixq, const Spin& same, const Spin*
     c.events_used = 0;
     int64_t& chunk_idx = c.chunk_counter;   // global: tile staging buffers alternate across calls too
     std::vector<K1Tile> tiles;
-    std::vector<SubTile> plain;
 
     auto run_chunks = [&](const std::vector<Item>& items, bool sym) -> int {
         size_t pos = 0;
         while (pos < items.size()) {
-            // ---- pack items into one chunk ----
-            tiles.clear();
-            plain.clear();
-            int64_t col = 0;
+            // ---- pack items into one chunk (planner.h) ----
             int need_rank = -1;
-            const size_t pos_end = std::min(items.size(), pos + (size_t)items_per_chunk(items[pos].kind));
-            while (pos < pos_end) {
-                const Item& it = items[pos];
-                const int64_t w = it.kind == 2 ? vbpad : vpad;
-                const int nblk = it.kind == 1 ? ((ca != 0.0) + (cs != 0.0)) : 1;
-                if (col + nblk * w > cap_cols) break;
-                if (gate) {
-                    need_rank = std::max(need_rank, (*gate->rank)[it.i]);
-                    if (it.kind != 2) need_rank = std::max(need_rank, (*gate->rank)[it.j]);
-                }
-                if (it.kind == 1 || it.kind == 3) {
-                    const double eij = ei_same_host[it.i] + ei_same_host[it.j];
-                    const long long c1 = col, c2 = (it.kind == 1 && ca != 0.0) ? col + w : col;
-                    // tile order (pair, x-block, a-block): consecutive CTAs share the ixq rows of their
-                    // x-block and the (Q|ja) columns of their pair while those are still in L2
-                    for (int xb = 0; xb < nxb; ++xb) {
-                        for (const auto& blk : blk_same) {
-                            const int64_t a0 = blk.first;
-                            const int nb = blk.second;
-                            const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, v - a0));
-                            K1Tile t;
-                            memset(&t, 0, sizeof(t));
-                            t.i1 = it.i; t.j1 = it.j; t.a1 = (int)a0; t.nb1 = nb;
-                            t.i2 = it.j; t.j2 = it.i; t.a2 = (int)a0; t.nb2 = nb;
-                            t.xb = xb; t.nv1 = t.nv2 = nv; t.e1 = t.e2 = eij;
-                            t.col1 = c1 + a0; t.col2 = c2 + a0;
-                            if (it.kind == 1) {
-                                t.ws1 = ca != 0.0 ? 0 : -1; t.p11 = ca; t.p12 = -ca;
-                                t.ws2 = cs != 0.0 ? 0 : -1; t.p21 = cs; t.p22 = cs;
-                            } else {
-                                t.ws1 = 0; t.p11 = 1.0; t.p12 = 0.0;
-                                t.ws2 = 1; t.p21 = asym_c; t.p22 = -s_same;   // (p21 = 0: out2 width falls back to nb2 == nb1)
-                            }
-                            t.mbv = thin_mbv(xb, t.nb1, t.nb2);
-                            tiles.push_back(t);
-                        }
-                    }
-                } else {
-                    const bool os = it.kind == 2;
-                    const int64_t vv_ = os ? other->nvir : v;
-                    const double eij = ei_same_host[it.i] + (os ? ei_other_host[it.j] : ei_same_host[it.j]);
-                    for (const auto& blk : (os ? blk_other : blk_same)) {
-                        const int64_t a0 = blk.first;
-                        const int nb = blk.second;
-                        const int nv = (int)std::max<int64_t>(0, std::min<int64_t>(8 * nb, vv_ - a0));
-                        plain.push_back({it.i, it.j, (int)a0, nb, os ? 1 : 0, os ? 1 : 0, nv, (long long)(col + a0),
-                                         os ? co : cd, eij});
-                    }
-                }
-                col += nblk * w;
-                ++pos;
-            }
+            const int64_t col = plan.next_chunk(items, pos, ei_same_host, ei_other_host, gate ? gate->rank : nullptr,
+                                                tiles, need_rank);
             if (col == 0) return fail(AGF2_B200_EINVAL, "workspace too small for one work item");
-            // two independent plain blocks share one CTA tile
-            std::stable_sort(plain.begin(), plain.end(), [](const SubTile& a, const SubTile& b) { return a.nb > b.nb; });
-            for (size_t k = 0; k < plain.size();) {
-                const SubTile& s1 = plain[k];
-                // only equal-width blocks share a CTA tile: k1_form is instantiated for (n, n) and (n, 0)
-                const SubTile* s2 = (k + 1 < plain.size() && plain[k + 1].nb == s1.nb) ? &plain[k + 1] : nullptr;
-                k += s2 ? 2 : 1;
-                for (int xb = 0; xb < nxb; ++xb) {
-                    K1Tile t;
-                    memset(&t, 0, sizeof(t));
-                    t.xb = xb;
-                    t.i1 = s1.i; t.j1 = s1.j; t.a1 = s1.a0; t.nb1 = s1.nb; t.bsel1 = s1.bsel; t.esel1 = s1.esel;
-                    t.nv1 = s1.nv; t.col1 = s1.col; t.p11 = s1.p; t.e1 = s1.eij; t.ws1 = 0;
-                    t.ws2 = -1;
-                    if (s2) {
-                        t.i2 = s2->i; t.j2 = s2->j; t.a2 = s2->a0; t.nb2 = s2->nb; t.bsel2 = s2->bsel; t.esel2 = s2->esel;
-                        t.nv2 = s2->nv; t.col2 = s2->col; t.p22 = s2->p; t.e2 = s2->eij; t.ws2 = 0;
-                    }
-                    t.mbv = thin_mbv(xb, t.nb1, t.nb2);
-                    tiles.push_back(t);
-                }
-            }
-            // longest tiles first: the block scheduler then packs the short ones into the tail of the launch
-            if (c.lpt_order)
-                std::stable_sort(tiles.begin(), tiles.end(),
-                                 [&](const K1Tile& a, const K1Tile& b) { return tile_work(a) > tile_work(b); });
 
             // ---- upload the tile list (double-buffered pinned staging) ----
             const int buf = (int)(chunk_idx & 1);
@@ -927,6 +704,59 @@ int64_t agf2_b200_launch_count(int reset) {
 int agf2_b200_last_stage_ms(double* ms4) {
     if (!ms4) return fail(AGF2_B200_EINVAL, "null pointer");
     for (int k = 0; k < 4; ++k) ms4[k] = g_ctx.last_ms[k];
+    return 0;
+}
+
+int agf2_b200_plan_stats(int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t nocc_b, int64_t nvir_b,
+                         int64_t istart, int64_t iend, double os_factor, double ss_factor, int uhf, int64_t part,
+                         int64_t nparts, int64_t* cover, int64_t* stats8)
+{
+    if (!stats8) return fail(AGF2_B200_EINVAL, "null pointer");
+    apply_env();
+    MomentPlan plan;
+    const bool has_b = uhf && nocc_b > 0 && nvir_b > 0;
+    // same coefficient convention as the moments entry points (RHF: c = os + ss, s = ss; UHF: c = s = ss, other os)
+    const double c_same = uhf ? ss_factor : os_factor + ss_factor, os_other = uhf ? os_factor : 0.0;
+    if (int r = plan.init(plan_config(), nphys, naux, nocc, nvir, has_b, nocc_b, nvir_b, istart, iend, c_same, ss_factor,
+                          os_other, part, nparts))
+        return fail(r, plan.error);
+    std::vector<double> e_same((size_t)nocc, 0.0), e_other((size_t)std::max<int64_t>(nocc_b, 1), 0.0);
+    std::vector<K1Tile> tiles;
+    int64_t n_chunks = 0, n_tiles = 0, n_thin = 0, max_cols = 0, max_items = 0;
+    const int64_t ncov = nocc + (has_b ? nocc_b : 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<Item>& items = pass ? plan.asym_items : plan.sym_items;
+        size_t pos = 0;
+        while (pos < items.size()) {
+            const size_t pos0 = pos;
+            int need_rank;
+            const int64_t col = plan.next_chunk(items, pos, e_same.data(), e_other.data(), nullptr, tiles, need_rank);
+            if (col == 0) return fail(AGF2_B200_EINVAL, "workspace too small for one work item");
+            ++n_chunks;
+            n_tiles += (int64_t)tiles.size();
+            max_cols = std::max(max_cols, col);
+            max_items = std::max<int64_t>(max_items, (int64_t)(pos - pos0));
+            for (const K1Tile& t : tiles) {
+                if (t.mbv > 0) ++n_thin;
+                const int nbo2 = (t.p21 != 0.0) ? t.nb1 : t.nb2;   // width of out2, as in the k1_form epilogue
+                if ((t.ws1 >= 0 && (t.col1 < 0 || t.col1 + 8 * t.nb1 > plan.cap_cols)) ||
+                    (t.ws2 >= 0 && (t.col2 < 0 || t.col2 + 8 * nbo2 > plan.cap_cols)))
+                    return fail(AGF2_B200_EINVAL, "planner bug: tile outside the workspace");
+                if (cover) {   // 8-column blocks of (x-block, i, j) formed: same spin in [0, nocc), other spin after
+                    if (t.nb1) cover[(int64_t)t.i1 * ncov + (t.bsel1 ? nocc + t.j1 : t.j1)] += t.nb1;
+                    if (t.nb2) cover[(int64_t)t.i2 * ncov + (t.bsel2 ? nocc + t.j2 : t.j2)] += t.nb2;
+                }
+            }
+        }
+    }
+    stats8[0] = plan.fact ? 1 : 0;
+    stats8[1] = n_chunks;
+    stats8[2] = n_tiles;
+    stats8[3] = n_thin;
+    stats8[4] = max_cols;
+    stats8[5] = plan.cap_cols;
+    stats8[6] = max_items;
+    stats8[7] = (int64_t)plan.nxb * (plan.vpad / 8);   // 8-column blocks of one complete (xi|ja) block
     return 0;
 }
 

@@ -33,7 +33,7 @@ SYMBOLS = [
     "agf2_b200_compress", "agf2_b200_eigh", "agf2_b200_launch_count", "agf2_b200_last_kernel_ms",
     "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap", "agf2_b200_last_stage_ms",
     "agf2_b200_set_coulomb_factorization", "agf2_b200_last_plan", "agf2_b200_build_part_loop_rhf_sharded",
-    "agf2_b200_build_part_loop_uhf_sharded",
+    "agf2_b200_build_part_loop_uhf_sharded", "agf2_b200_plan_stats",
 ]
 
 
@@ -63,6 +63,8 @@ _libagf2.agf2_b200_last_kernel_ms.argtypes = [ctypes.POINTER(_dbl), ctypes.POINT
 _libagf2.agf2_b200_set_device.argtypes = [ctypes.c_int]
 _libagf2.agf2_b200_set_workspace_bytes.argtypes = [_i64]
 _libagf2.agf2_b200_set_simple_kernels.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_plan_stats.argtypes = [_i64] * 8 + [_dbl, _dbl, ctypes.c_int, _i64, _i64, ctypes.POINTER(_i64),
+                                          ctypes.POINTER(_i64)]
 _libagf2.agf2_b200_build_part_loop_rhf.argtypes = [_in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _out2, _out2]
 _libagf2.agf2_b200_build_part_loop_rhf_sharded.argtypes = [_in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _i64, _i64,
                                                                                                 _out2, _out2]
@@ -120,6 +122,22 @@ def last_plan():
     out = (_i64 * 6)()
     check(_libagf2.agf2_b200_last_plan(out))
     return dict(zip(("factorised", "pair", "diag", "os", "asym", "k1_launches"), [int(x) for x in out]))
+
+
+def plan_stats(nphys, nocc, nvir, naux, nocc_b=0, nvir_b=0, istart=0, iend=None, os_factor=1.0, ss_factor=1.0,
+               uhf=False, part=0, nparts=1, cover=None):
+    """Work plan of a moments call (host only, no GPU): dict of planner statistics; ``cover`` (int64,
+    nocc x (nocc + nocc_b)) accumulates how many 8-column blocks of every (xi|ja) block this part forms."""
+    iend = nocc if iend is None else iend
+    out = (_i64 * 8)()
+    cptr = None
+    if cover is not None:
+        assert cover.dtype == np.int64 and cover.flags.c_contiguous and cover.shape == (nocc, nocc + (nocc_b if uhf else 0))
+        cptr = cover.ctypes.data_as(ctypes.POINTER(_i64))
+    check(_libagf2.agf2_b200_plan_stats(nphys, nocc, nvir, naux, nocc_b, nvir_b, istart, iend, os_factor, ss_factor,
+                                        1 if uhf else 0, part, nparts, cptr, out))
+    keys = ("factorised", "chunks", "tiles", "thin_tiles", "max_cols", "cap_cols", "max_items", "blocks_per_pair")
+    return dict(zip(keys, [int(x) for x in out]))
 
 
 def set_coulomb_factorization(mode):

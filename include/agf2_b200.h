@@ -181,6 +181,16 @@ int agf2_b200_last_stage_ms(double *ms4);
  * [5] the number of k1_form launches (= chunks). */
 int agf2_b200_last_plan(int64_t *info6);
 
+/* The work plan of a moments call, computed on the host without touching the GPU (same planner code the launches use):
+ * cover (optional, nocc x (nocc [+ nocc_b]) int64, accumulated into): number of 8-column blocks of every (xi|ja) block
+ * (i, j) -- same spin in columns [0, nocc), other spin after -- that this part's k1_form tiles form, summed over
+ * x-blocks; stats8 = { Coulomb factorisation used, chunks, CTA tiles, thin tiles, widest chunk (columns), workspace
+ * columns, most items in a chunk, 8-column blocks of one complete (xi|ja) block }.  uhf != 0: the UHF channel
+ * convention of agf2_b200_moments_uhf_dev (nocc/nvir = same spin, nocc_b/nvir_b = other spin). */
+int agf2_b200_plan_stats(int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t nocc_b, int64_t nvir_b,
+                         int64_t istart, int64_t iend, double os_factor, double ss_factor, int uhf, int64_t part,
+                         int64_t nparts, int64_t *cover, int64_t *stats8);
+
 /* Coulomb factorisation (default on): every Coulomb-type term  sum_ija w X_ija X_ija^T (e_i+e_j-e_a)^n  of
  * auxgf/lib/libagf2/optragf2.c:206-290 / optuagf2.c:211-314 is evaluated as  sum_i ixq_i (e_i^n M0 + n M1) ixq_i^T
  * with the naux x naux matrices M0 = sum_ja w q_ja q_ja^T, M1 = sum_ja w (e_j - e_a) q_ja q_ja^T, so that only the
