@@ -181,9 +181,11 @@ def main():
         cb["value"] = val
         print(json.dumps({
             "impl": "reference", "metric": "agf2_moment_build_seconds_per_iter", "value": val, "unit": "s",
-            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload}, "tflops": flops_build / val * 1e-12, "cpu_baseline": cb,
+            "config": {"workload": workload, "l2": "n/a (host cores)",
+                       "parallelism": "reference OpenMP loop over poles on %d host threads (no GPU)" % cb["cores"]},
+            "tflops": flops_build / val * 1e-12, "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
