@@ -7,13 +7,15 @@
 //                     out1 = p11*acc1 + p12*acc2,  out2 = p21*acc1 + p22*acc2
 //                 written to the L2-resident workspace W[x][col] together with the energy weights
 //                 E[col] = e_i + e_j - e_a.  For a pole pair i>j, (acc1, acc2) = (X_ij, X_ji) and
-//                 (out1, out2) = (sqrt(os/2+ss) (X_ij - X_ji), sqrt(os/2) (X_ij + X_ji)): the
-//                 2(xi|ja)-(xj|ia) exchange combination in pair-symmetric (SYRK) form, each integral
-//                 formed once.  Replaces auxgf/lib/libagf2/optragf2.c:121-199.
-//   k2_moment   : vv += W W^T, vev += W diag(E) W^T for one (128 x 64) output tile and one K slice
-//                 (same DMMA/TMA pipeline; E applied to the A fragments in registers), reduced into
-//                 the accumulators with red.global.add.f64.  Symmetric chunks only visit upper-triangle
-//                 tiles.  Replaces optragf2.c:206-290.
+//                 out1 = sqrt(ss) (X_ij - X_ji)  [all-pairs route: also out2 = sqrt(os/2) (X_ij + X_ji)]:
+//                 the 2(xi|ja)-(xj|ia) exchange combination in pair-symmetric (SYRK) form, each integral
+//                 formed once.  A ragged last x-block (<= 80 valid rows) uses the thin-tile warp mapping
+//                 (k1_mainloop_thin).  Replaces auxgf/lib/libagf2/optragf2.c:121-199.
+//   k2_moment   : acc_vv += A' B^T, acc_vev += A'' B^T on 128 x 64 output tiles, stream-K over the SMs (same
+//                 DMMA/TMA pipeline; weights applied to the A fragments in registers), reduced into the
+//                 accumulators with red.global.add.f64.  Three uses: pair-loop moments W W^T / W diag(E) W^T
+//                 (optragf2.c:206-290, upper-triangle tiles only), the M0/M1 build and the Coulomb step of the
+//                 Coulomb factorisation (see the comment above the kernel).
 //   k3_finalize : mirrors the upper triangle, adds the non-symmetric part, accumulates into vv/vev.
 //   *_simple    : naive one-thread-per-element versions of k1/k2 driven by the same tile lists (debug).
 #pragma once
