@@ -88,3 +88,45 @@ def test_plan_errors():
         lib.plan_stats(10, 4, 5, 20, part=2, nparts=2)
     with pytest.raises(lib.Agf2B200Error):
         lib.plan_stats(10, 4, 5, 20, istart=3, iend=9)
+
+
+def test_coverage_property_random_shapes():
+    """Randomised: for any shape, slice, sharding, SCS factors and route, the union over parts of the k1_form tiles forms
+    exactly the (xi|ja) blocks the algorithm needs -- X_ij and X_ji for every pole pair with at least one member in the
+    slice (the exchange term), X_ii only on the all-pairs route (Coulomb through the pair loop) -- each exactly once."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(o=st.integers(1, 11), v=st.integers(1, 70), p=st.integers(1, 300), naux=st.integers(1, 200),
+           nparts=st.integers(1, 5), mode=st.sampled_from([0, 1]), os_f=st.sampled_from([0.0, 1.0, 1.2]),
+           ss_f=st.sampled_from([0.0, 1.0, 1.0 / 3.0]), data=st.data())
+    def check(o, v, p, naux, nparts, mode, os_f, ss_f, data):
+        i0 = data.draw(st.integers(0, o))
+        i1 = data.draw(st.integers(i0, o))
+        lib.set_coulomb_factorization(mode)
+        try:
+            cover = np.zeros((o, o), dtype=np.int64)
+            stats = [lib.plan_stats(p, o, v, naux, istart=i0, iend=i1, os_factor=os_f, ss_factor=ss_f, part=k,
+                                    nparts=nparts, cover=cover) for k in range(nparts)]
+        finally:
+            lib.set_coulomb_factorization(2)
+        full = stats[0]["blocks_per_pair"]
+        assert full == ((p + 127) // 128) * ((v + 7) // 8)
+        fact = stats[0]["factorised"]
+        inside = np.zeros(o, dtype=bool); inside[i0:i1] = True
+        expect = np.zeros((o, o), dtype=np.int64)
+        for i in range(o):
+            for j in range(o):
+                if i == j:
+                    need = inside[i] and not fact and os_f != 0.0                 # DIAG item
+                elif inside[i] and inside[j]:
+                    need = ss_f != 0.0 or (not fact and os_f != 0.0)              # PAIR item (A, and S off-route)
+                elif inside[i] or inside[j]:
+                    need = not (fact and ss_f == 0.0)                             # ASYM item
+                else:
+                    need = False
+                expect[i, j] = full if need else 0
+        assert np.array_equal(cover, expect), (o, v, p, i0, i1, nparts, mode, os_f, ss_f)
+        assert all(s["max_cols"] <= s["cap_cols"] for s in stats)
+
+    check()
