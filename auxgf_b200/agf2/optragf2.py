@@ -11,8 +11,9 @@ What changed underneath:
 * every dense eigensolve of the extended Fock matrix goes through cuSOLVER dsyevd (``Aux.eig``);
 * ``ss_factor``/``os_factor`` are honoured (the reference accepts and ignores them, optragf2.py:33-34,
   hard-coded 2/-1 at :264-268); the defaults 1/1 reproduce the reference;
-* under ``torchrun`` (torch.distributed initialised) the pair-work items of the moment build are dealt
-  round-robin to the ranks and vv/vev are summed with ONE all-reduce per sector, replacing the mpi4py
+* with one process per GPU (``torchrun`` or any launcher setting RANK / WORLD_SIZE / LOCAL_RANK) the pair-work
+  items of the moment build are dealt round-robin to the ranks and the packed [vv|vev] is summed with ONE NCCL
+  all-reduce per sector INSIDE the library (``auxgf_b200.util.mpi`` owns the communicator), replacing the mpi4py
   split + Reduce/Bcast of ``auxgf/mpi/agf2/optragf2.py:370-395``.
 """
 import numpy as np
@@ -20,7 +21,7 @@ import numpy as np
 from auxgf_b200 import backend
 from auxgf_b200.aux import Aux, energy
 from auxgf_b200.agf2.fock import fock_loop_rhf
-from auxgf_b200.util import Timer, find_chempot, record_energy, record_time
+from auxgf_b200.util import Timer, find_chempot, mpi, record_energy, record_time
 
 _DEFAULTS = {
     "maxiter": 50, "etol": 1e-6, "wtol": 1e-12, "damping": 0.0, "delay_damping": 0, "dtol": 1e-8,
@@ -39,31 +40,6 @@ def _set_options(options, **kwargs):
                              "maxiter": options["fock_maxiter"], "maxruns": options["fock_maxruns"],
                              "verbose": options["verbose"]}
     return options
-
-
-def dist_info():
-    """(rank, world) of the torch.distributed job, (0, 1) when not initialised."""
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_rank(), dist.get_world_size()
-    except ImportError:
-        pass
-    return 0, 1
-
-
-def allreduce_moments(t):
-    """One all-reduce (NCCL over NVLink when the tensor is on the GPU) of the packed [vv|vev] buffer."""
-    rank, world = dist_info()
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        if isinstance(t, torch.Tensor):
-            dist.all_reduce(t)
-        else:                       # host buffer (CPU test-suite over gloo)
-            buf = torch.from_numpy(t.a)
-            dist.all_reduce(buf)
-    return t
 
 
 def pack_tril(a):
@@ -86,7 +62,7 @@ class OptRAGF2:
     def __init__(self, rhf, **kwargs):
         self.hf = rhf
         self._timer = Timer()
-        self.options = {"dm0": None, "frozen": (0, 0), "verbose": dist_info()[0] == 0}
+        self.options = {"dm0": None, "frozen": (0, 0), "verbose": mpi.rank() == 0}
         self.options = _set_options(self.options, **kwargs)
         self.verbose = self.options["verbose"]
         if tuple(self.options["frozen"]) != (0, 0):
@@ -144,9 +120,8 @@ class OptRAGF2:
         (optragf2.py:217-280).  ``eri``: a staged ``DeviceERI`` (preferred) or the host DF tensor."""
         be = backend.get()
         staged = eri if hasattr(eri, "moments_rhf") else be.stage_eri(np.asarray(eri), gf_occ.nphys, sym_in=sym_in)
-        rank, world = dist_info()
-        mom = staged.moments_rhf(gf_occ, gf_vir, os_factor=os_factor, ss_factor=ss_factor, part=rank, nparts=world)
-        mom = allreduce_moments(mom)
+        # this rank's share of the pair-work items + one all-reduce over the ranks, both inside the staged handle
+        mom = staged.moments_rhf(gf_occ, gf_vir, os_factor=os_factor, ss_factor=ss_factor)
         e, c = staged.compress(mom)            # b = chol(vv)^T ... c = b^T u        (optragf2.py:270-276)
         return gf_occ.new(e, c)
 
@@ -234,7 +209,7 @@ class OptRAGF2:
                 if e_dif < etol and self.converged:
                     break
                 self.converged = e_dif < etol
-            if self.options["checkpoint"] and dist_info()[0] == 0:
+            if self.options["checkpoint"] and mpi.rank() == 0:
                 self._write_checkpoint()
         self._log("Auxiliary GF2 %s after %d iterations." % ("converged" if self.converged else "failed to converge",
                                                             self.iteration))

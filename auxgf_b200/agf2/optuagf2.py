@@ -8,7 +8,7 @@ from auxgf_b200 import backend
 from auxgf_b200.aux import Aux, energy
 from auxgf_b200.agf2 import optragf2
 from auxgf_b200.agf2.fock import fock_loop_uhf
-from auxgf_b200.agf2.optragf2 import OptRAGF2, allreduce_moments, dist_info, pack_tril
+from auxgf_b200.agf2.optragf2 import OptRAGF2, pack_tril
 from auxgf_b200.util import record_energy, record_time
 
 
@@ -38,13 +38,10 @@ class OptUAGF2(OptRAGF2):
         be = backend.get()
         nphys = gf_occ[0].nphys
         staged = tuple(e if hasattr(e, "sector") else be.stage_eri(np.asarray(e), nphys, sym_in=sym_in) for e in eri)
-        rank, world = dist_info()
 
         def _build_part(s):
             o = tuple(gf_occ[::s]); v = tuple(gf_vir[::s]); er = tuple(staged[::s])
-            mom = er[0].moments_uhf(er[0], er[1], o, v, os_factor=os_factor, ss_factor=ss_factor,
-                                    part=rank, nparts=world)
-            mom = allreduce_moments(mom)
+            mom = er[0].moments_uhf(er[0], er[1], o, v, os_factor=os_factor, ss_factor=ss_factor)
             e, c = er[0].compress(mom)
             return o[0].new(e, c)
 

@@ -409,7 +409,9 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
 // Operands are 3-D tensor maps (k, row, outer) -- or (k, outer, row) when swap is set -- with 16 x 64 x 1 boxes;
 // the K iteration `kit` addresses outer = kit / nk_inner, k = 16 (kit % nk_inner); weights are indexed 16 kit + k.
 struct K2Tile {
-    int xb, yb;   // rows [128*xb, +128) of operand A, rows [64*yb, +64) of operand B
+    int xb, yb;   // rows [a_row_step*xb, +128) of operand A, rows [64*yb, +64) of operand B
+    int zb;       // batch index (general GEMM launches only: outer TMA coordinate of the batched operands)
+    int pad_;
 };
 
 struct K2Params {
@@ -420,14 +422,24 @@ struct K2Params {
     double* acc_vv;
     double* acc_vev;
     long long ldacc;
+    double* partial;         // stream-K scratch, gridDim.x slots of 2 x 128 x 64 doubles (nullptr: every partial
+                             // tile goes straight into the accumulators with red.global.add -- order not fixed)
     int ntiles, nk_inner, n_outer;
     int swap_a, swap_b;      // operand maps are (k, outer, row) instead of (k, row, outer)
+    int a_row_off;
     int b_k_off, b_outer_off, b_row_off;
     int rows_valid, cols_valid;   // logical extent of the output (masks out padded warps / column blocks)
     int sym;                 // only the blocks touching the upper triangle are computed
     int mask;                // 0: every warp computes all 8 column blocks of every tile; 1: warps with nothing
-                             // to do on an edge tile skip it; 2: partially needed warps also skip column blocks
-                             // (predicated DMMAs -- measured slower than computing the padding)
+                             // to do on an edge tile skip it
+    // ---- general GEMM launches (kGen instantiation only) ----
+    int a_row_step;          // rows of operand A per unit of xb: 128, or 256 when the second accumulator is the
+                             // product of rows +128 of the same operand (plain C = A B^T on 256 x 64 tiles)
+    int transpose_out;       // output element (row, col) lives at acc[col * ldacc + row]
+    int store;               // the segment that starts a tile stores instead of accumulating (no memset needed)
+    int a_batch, b_batch;    // add the tile's zb to the outer coordinate of operand A / B
+    long long out_batch_stride;   // output offset per unit of zb
+    int vev_rows_valid;      // valid rows of the second accumulator (a_row_step == 256: rows_valid - 128 - 256 xb)
 };
 
 constexpr int kK2StageBytes = kTileM * kKB * 8 + kTileN * kKB * 8 + 1024;  // A 16K + B 8K + weights (2 x 128 B, padded)
@@ -448,7 +460,7 @@ __host__ __device__ inline void k2_warp_range(int xb, int yb, int warp, int rows
     if (row0 >= rows_valid) hi = 0;
     if (sym && row0 > col0) lo = (row0 - col0) / 8;   // blocks entirely below the diagonal are skipped
     if (lo >= hi) lo = hi = 0;
-    else if (mask < 2) { lo = 0; hi = 8; }
+    else { lo = 0; hi = 8; }      // a warp either computes all 8 column blocks or skips the tile
 }
 // Cost of a tile in sixteenths of a full one: the busiest SM sub-partition (warps w and w + 4 share one).
 // A partially masked warp still issues its predicated-off DMMAs, so it never costs less than half a full one;
@@ -485,7 +497,23 @@ __device__ __forceinline__ void k2_boundary(const int* __restrict__ prefix, int 
     if (tile < ntiles) kit = (int)((u - (long long)prefix[tile] * nk) / (prefix[tile + 1] - prefix[tile]));
 }
 
-template <bool kDual, bool kW0>
+// Address of output element (r, c) of tile t (r in [0,128), c in [0,64)) of accumulator `which` (0: vv, 1: vev);
+// general launches: nullptr when the element lies outside the logical output.
+template <bool kGen>
+__device__ __forceinline__ double* k2_out_ptr(const K2Params& p, const K2Tile& t, int r, int c, int which)
+{
+    double* base = which ? p.acc_vev : p.acc_vv;
+    if (!kGen) return base + ((long long)t.xb * kTileM + r) * p.ldacc + (long long)t.yb * kTileN + c;
+    const long long row = (long long)t.xb * p.a_row_step + r;
+    const long long col = (long long)t.yb * kTileN + c;
+    if (row >= (which ? p.vev_rows_valid : p.rows_valid) || col >= p.cols_valid) return nullptr;
+    base += (long long)t.zb * p.out_batch_stride;
+    return p.transpose_out ? base + col * p.ldacc + row : base + row * p.ldacc + col;
+}
+
+// kGen: general GEMM launches (guarded / transposed / batched output, 256-row plain-GEMM tiles) -- instantiated
+// with kDual only; the moment launches keep the unguarded epilogue on padded accumulators.
+template <bool kDual, bool kW0, bool kGen = false>
 __global__ void __launch_bounds__(kThreads, 1)
 k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ K2Params p)
@@ -500,8 +528,11 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     uint8_t* const gbase = smem_raw + (base - smem_u32(smem_raw));
 
     // stream-K: the (tile, k-iteration) space, weighted by tile cost, is cut into gridDim.x equal ranges so
-    // that every SM gets the same amount of DMMA work whatever the tile count; a CTA flushes its accumulators
-    // (red.global.add) whenever its range crosses a tile boundary.
+    // that every SM gets the same amount of DMMA work whatever the tile count.  A CTA flushes its accumulators
+    // whenever its range crosses a tile boundary: the segment that STARTS a tile (k = 0) adds into the
+    // accumulators (one adder per element and launch), every other segment -- at most one per CTA, its first --
+    // goes to the CTA's slot of the `partial` scratch and k2_fixup adds the slots in CTA order afterwards, so
+    // that the summation order is fixed (bit-reproducible moments).
     const int nk_total = p.nk_inner * p.n_outer;
     int tile, kit, tile_end, kit_end;
     k2_boundary(p.cost_prefix, p.ntiles, nk_total, blockIdx.x, gridDim.x, tile, kit);
@@ -526,8 +557,8 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             tma_prefetch_desc(&mapA0);
             tma_prefetch_desc(&mapB);
             if (kDual) tma_prefetch_desc(&mapA1);
-            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + kKB * 8 + (kW0 ? kKB * 8 : 0) +
-                                       (kDual ? kTileM * kKB * 8 : 0);
+            constexpr uint32_t bytes = kTileM * kKB * 8 + kTileN * kKB * 8 + (kGen ? 0 : kKB * 8) +
+                                       (kW0 ? kKB * 8 : 0) + (kDual ? kTileM * kKB * 8 : 0);
             K2Tile t = p.tiles[tile];
             int outer = kit / p.nk_inner, ki = kit % p.nk_inner;
             for (int j = 0; j < nk; ++j) {
@@ -537,22 +568,25 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 const uint32_t fb = bar_full + 8 * s;
                 mbar_expect_tx(fb, bytes);
                 const int k0 = ki * kKB;
-                const int ra = t.xb * kTileM, rb = t.yb * kTileN + p.b_row_off, ob = outer + p.b_outer_off;
+                const int ra = t.xb * (kGen ? p.a_row_step : kTileM) + p.a_row_off;
+                const int rb = t.yb * kTileN + p.b_row_off;
+                const int oa = outer + ((kGen && p.a_batch) ? t.zb : 0);
+                const int ob = outer + p.b_outer_off + ((kGen && p.b_batch) ? t.zb : 0);
                 if (p.swap_a) {
-                    tma_load_3d(st, &mapA0, k0, outer, ra, fb);
-                    tma_load_3d(st + 8192, &mapA0, k0, outer, ra + 64, fb);
+                    tma_load_3d(st, &mapA0, k0, oa, ra, fb);
+                    tma_load_3d(st + 8192, &mapA0, k0, oa, ra + 64, fb);
                 } else {
-                    tma_load_3d(st, &mapA0, k0, ra, outer, fb);
-                    tma_load_3d(st + 8192, &mapA0, k0, ra + 64, outer, fb);
+                    tma_load_3d(st, &mapA0, k0, ra, oa, fb);
+                    tma_load_3d(st + 8192, &mapA0, k0, ra + 64, oa, fb);
                 }
                 if (kDual) {
-                    tma_load_3d(st + kOffA1, &mapA1, k0, ra, outer, fb);
-                    tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, ra + 64, outer, fb);
+                    tma_load_3d(st + kOffA1, &mapA1, k0, ra, oa, fb);
+                    tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, ra + 64, oa, fb);
                 }
                 if (p.swap_b) tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, ob, rb, fb);
                 else tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, rb, ob, fb);
                 const long long wi = ((long long)outer * p.nk_inner + ki) * kKB;
-                bulk_load_1d(st + kOffW, p.w1 + wi, kKB * 8, fb);
+                if (!kGen) bulk_load_1d(st + kOffW, p.w1 + wi, kKB * 8, fb);   // (general GEMM: no weights)
                 if (kW0) bulk_load_1d(st + kOffW + 128, p.w0 + wi, kKB * 8, fb);
                 if (++ki == p.nk_inner) {
                     ki = 0;
@@ -585,7 +619,8 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     auto load_unit = [&](const uint8_t* st, int u) {
         const int ks = u >> 1, half = u & 1;
         if (half == 0) {
-            const double2 ev = *reinterpret_cast<const double2*>(st + kOffW + (4 * ks + tig) * 16);
+            double2 ev = make_double2(0.0, 0.0);
+            if (!kGen) ev = *reinterpret_cast<const double2*>(st + kOffW + (4 * ks + tig) * 16);
             double2 ev0;
             if (kW0) ev0 = *reinterpret_cast<const double2*>(st + kOffW + 128 + (4 * ks + tig) * 16);
 #pragma unroll
@@ -593,8 +628,12 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                 double2 a = *reinterpret_cast<const double2*>(st + a_row + mb * 1024 + sw[ks]);
                 if (kDual) {
                     const double2 a1 = *reinterpret_cast<const double2*>(st + kOffA1 + a_row + mb * 1024 + sw[ks]);
-                    fe[ks][mb].x = fma(a.x, ev.x, a1.x);
-                    fe[ks][mb].y = fma(a.y, ev.y, a1.y);
+                    if (kGen) {
+                        fe[ks][mb] = a1;
+                    } else {
+                        fe[ks][mb].x = fma(a.x, ev.x, a1.x);
+                        fe[ks][mb].y = fma(a.y, ev.y, a1.y);
+                    }
                 } else {
                     fe[ks][mb].x = a.x * ev.x;
                     fe[ks][mb].y = a.y * ev.y;
@@ -624,31 +663,14 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             }
         }
     };
-    // edge tiles (diagonal, padded last row / column): only the column blocks [lo, hi) of this warp
-    auto compute_unit_masked = [&](int u, int lo, int hi) {
-        const int ks = u >> 1, half = u & 1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int nb = 4 * half + j;
-            if (nb >= lo && nb < hi) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].x, fb[half][j].x);
-                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].x, fb[half][j].x);
-                    dmma884(cvv[mb][nb][0], cvv[mb][nb][1], fa[ks][mb].y, fb[half][j].y);
-                    dmma884(cvev[mb][nb][0], cvev[mb][nb][1], fe[ks][mb].y, fb[half][j].y);
-                }
-            }
-        }
-    };
 
     K2Tile t = p.tiles[tile];
     int lo, hi;
-    k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, p.mask, lo, hi);
+    k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, kGen ? 0 : p.mask, lo, hi);
     mbar_wait(bar_full, 0);
     load_unit(gbase, 0);
-    // One iteration = one pipeline stage.  kMode 0: all 8 column blocks (the hot loop), 1: blocks [lo, hi),
-    // 2: nothing to compute for this warp (it only keeps the pipeline moving).
+    // One iteration = one pipeline stage.  kMode 0: this warp computes the tile, 2: it has nothing to compute on
+    // this (edge) tile and only keeps the pipeline moving.
     auto iteration = [&](int it, auto mode) {
         constexpr int kMode = decltype(mode)::value;
         const int s = it % kStages;
@@ -663,8 +685,7 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                     mbar_wait(bar_full + 8 * s2, ((it + 1) / kStages) & 1);
                     load_unit(gbase + s2 * kStageBytes, 0);
                 }
-                if (kMode == 0) compute_unit(u);
-                else compute_unit_masked(u, lo, hi);
+                compute_unit(u);
             }
         }
         if (kMode == 2 && it + 1 < nk) {
@@ -678,32 +699,109 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     int it = 0;
     while (it < nk) {
         const int seg_end = min(nk, it + nk_total - kit);   // this tile's share of the range
-        if (lo == 0 && hi == 8) { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 0>()); }
-        else if (hi > lo) { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 1>()); }
+        const bool owner = kit == 0;                        // this segment starts the tile
+        if (hi > lo) { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 0>()); }
         else { for (; it < seg_end; ++it) iteration(it, std::integral_constant<int, 2>()); }
-        // split-K / cross-chunk reduction: warp-level fragments straight into the global accumulators
-        const long long x0 = (long long)t.xb * kTileM + 16 * warp;
-        const long long y0 = (long long)t.yb * kTileN;
+        if (!owner && p.partial != nullptr) {
+            // partial tile: fragments in register order into this CTA's slot (coalesced); masked blocks as zeros
+            double* const slot = p.partial + (size_t)blockIdx.x * (2 * kTileM * kTileN) + lane;
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-            const long long row = x0 + 8 * mb + pg;
+            for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-            for (int nb = 0; nb < 8; ++nb)
-                if (nb >= lo && nb < hi) {
+                for (int nb = 0; nb < 8; ++nb) {
+                    const bool on = nb >= lo && nb < hi;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const long long col = y0 + 8 * nb + pi8(2 * tig + h);
-                        red_add_f64(p.acc_vv + row * p.ldacc + col, cvv[mb][nb][h]);
-                        red_add_f64(p.acc_vev + row * p.ldacc + col, cvev[mb][nb][h]);
+                        const int idx = (((warp * 2 + mb) * 8 + nb) * 2 + h) * 32;
+                        slot[idx] = on ? cvv[mb][nb][h] : 0.0;
+                        slot[kTileM * kTileN + idx] = on ? cvev[mb][nb][h] : 0.0;
                         cvv[mb][nb][h] = 0.0;
                         cvev[mb][nb][h] = 0.0;
                     }
                 }
+        } else {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const int r = 16 * warp + 8 * mb + pg;
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb)
+                    if (nb >= lo && nb < hi) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = 8 * nb + pi8(2 * tig + h);
+                            double* const d0 = k2_out_ptr<kGen>(p, t, r, c, 0);
+                            double* const d1 = k2_out_ptr<kGen>(p, t, r, c, 1);
+                            if (kGen) {
+                                if (p.store && owner) {
+                                    if (d0) *d0 = cvv[mb][nb][h];
+                                    if (d1) *d1 = cvev[mb][nb][h];
+                                } else {
+                                    if (d0) red_add_f64(d0, cvv[mb][nb][h]);
+                                    if (d1) red_add_f64(d1, cvev[mb][nb][h]);
+                                }
+                            } else {
+                                red_add_f64(d0, cvv[mb][nb][h]);
+                                red_add_f64(d1, cvev[mb][nb][h]);
+                            }
+                            cvv[mb][nb][h] = 0.0;
+                            cvev[mb][nb][h] = 0.0;
+                        }
+                    }
+            }
         }
         kit = 0;
         if (it < nk) {
             t = p.tiles[++tile];
-            k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, p.mask, lo, hi);
+            k2_warp_range(t.xb, t.yb, warp, p.rows_valid, p.cols_valid, p.sym, kGen ? 0 : p.mask, lo, hi);
+        }
+    }
+}
+
+// Adds the partial-tile slots of a k2_moment launch (grid G) into the accumulators, slot after slot in CTA order.
+// CTA b of this kernel handles the tile CTA b of k2_moment started in mid-tile, unless CTA b - 1 did so too (then
+// that CTA's fixup block walks all the slots of the tile).
+template <bool kGen>
+__global__ void __launch_bounds__(256)
+k2_fixup(const __grid_constant__ K2Params p, int G)
+{
+    __shared__ int s_slots[160];
+    __shared__ int s_n;
+    const int nk_total = p.nk_inner * p.n_outer;
+    const int b = blockIdx.x;
+    int tile, kit;
+    k2_boundary(p.cost_prefix, p.ntiles, nk_total, b, G, tile, kit);
+    if (kit == 0 || tile >= p.ntiles) return;
+    if (b > 0) {
+        int tp, kp;
+        k2_boundary(p.cost_prefix, p.ntiles, nk_total, b - 1, G, tp, kp);
+        if (tp == tile && kp > 0) return;      // CTA b - 1 walks this tile's slots
+    }
+    if (threadIdx.x == 0) {
+        int n = 0, tc = tile, kc = kit;
+        for (int s = b; s < G; ++s) {           // slots of the CTAs that started inside this tile, in CTA order
+            int tn, kn;
+            k2_boundary(p.cost_prefix, p.ntiles, nk_total, s + 1, G, tn, kn);
+            if ((tn != tc || kn != kc) && n < 160) s_slots[n++] = s;   // (an empty range wrote no slot)
+            if (tn != tile || kn == 0) break;
+            tc = tn; kc = kn;
+        }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const K2Tile t = p.tiles[tile];
+    for (int idx = threadIdx.x; idx < kTileM * kTileN; idx += blockDim.x) {
+        const int lane = idx & 31, h = (idx >> 5) & 1, nb = (idx >> 6) & 7, mb = (idx >> 9) & 1, warp = idx >> 10;
+        const int r = 16 * warp + 8 * mb + pi8(lane >> 2);
+        const int c = 8 * nb + pi8(2 * (lane & 3) + h);
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            double* const d = k2_out_ptr<kGen>(p, t, r, c, which);
+            if (d == nullptr) continue;
+            double v = *d;
+            for (int k = 0; k < n; ++k)
+                v += p.partial[(size_t)s_slots[k] * (2 * kTileM * kTileN) + which * (kTileM * kTileN) + idx];
+            *d = v;
         }
     }
 }
@@ -720,13 +818,13 @@ __global__ void fill_m_weights(double* __restrict__ w0, double* __restrict__ w1,
     w0[(long long)j * kpad + a] = w;
     w1[(long long)j * kpad + a] = (a < v) ? w * (ej[j] - ea[a]) : 0.0;
 }
-// M = [M0 | M1] (n rows, two n_pad-wide halves, pitch ld) was accumulated on its upper triangle: fill the lower one
-__global__ void mirror_m(double* __restrict__ m, int n, long long n_pad, long long ld)
+// M0, M1 (n x n, pitch ld) were accumulated on their upper triangles: fill the lower ones
+__global__ void mirror_m(double* __restrict__ m0, double* __restrict__ m1, int n, long long ld)
 {
     const int c = blockIdx.y * blockDim.x + threadIdx.x, r = blockIdx.x;   // rows on grid.x: naux may exceed 65535
     if (c < r && c < n) {
-        m[(long long)r * ld + c] = m[(long long)c * ld + r];
-        m[(long long)r * ld + n_pad + c] = m[(long long)c * ld + n_pad + r];
+        m0[(long long)r * ld + c] = m0[(long long)c * ld + r];
+        m1[(long long)r * ld + c] = m1[(long long)c * ld + r];
     }
 }
 // Coulomb step: we[il, k] = e_{i0 + il}
@@ -737,23 +835,51 @@ __global__ void fill_e_weights(double* __restrict__ we, const double* __restrict
 }
 
 // ---- K3: finalize ------------------------------------------------------------------------------
-// out[x][y] += (x <= y ? S[x][y] : S[y][x]) + A[x][y]      (S: symmetric-chunk accumulator, upper
-// triangle valid; A: accumulator of the non-symmetric chunks, may be null)
-__global__ void k3_finalize(const double* __restrict__ s_vv, const double* __restrict__ s_vev,
-                            const double* __restrict__ a_vv, const double* __restrict__ a_vev,
+// out[x][y] += sum over accumulator sets s (one per stream, fixed order) of
+//              (x <= y ? S_s[x][y] : S_s[y][x]) + A_s[x][y]
+// (S: symmetric-chunk accumulator, upper triangle valid; A: accumulator of the non-symmetric chunks).
+// Set s lives at acc + 4 s n: [S_vv | S_vev | A_vv | A_vev], n = ldacc^2.
+__global__ void k3_finalize(const double* __restrict__ acc, long long n, int nsets, int has_asym,
                             long long ldacc, int nphys, double* __restrict__ vv, double* __restrict__ vev)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     const int x = blockIdx.y;
     if (y >= nphys) return;
     const long long u = (x <= y) ? (x * ldacc + y) : (y * ldacc + x);
-    double r0 = s_vv[u], r1 = s_vev[u];
-    if (a_vv != nullptr) {
-        r0 += a_vv[x * ldacc + y];
-        r1 += a_vev[x * ldacc + y];
+    double r0 = 0.0, r1 = 0.0;
+    for (int s = 0; s < nsets; ++s) {
+        const double* a = acc + 4 * s * n;
+        r0 += a[u];
+        r1 += a[n + u];
+        if (has_asym) {
+            r0 += a[2 * n + x * ldacc + y];
+            r1 += a[3 * n + x * ldacc + y];
+        }
     }
     vv[(long long)x * nphys + y] += r0;
     vev[(long long)x * nphys + y] += r1;
+}
+
+// vv += packed[0 : n], vev += packed[n : 2n]   (after the all-reduce of the packed moments)
+__global__ void add_packed(const double* __restrict__ packed, long long n, double* __restrict__ vv, double* __restrict__ vev)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { vv[k] += packed[k]; vev[k] += packed[n + k]; }
+}
+
+// Tile list of a general GEMM launch, generated on the device: tile t = (xb, yb, zb) with xb fastest, uniform cost.
+__global__ void gen_gemm_tiles(K2Tile* __restrict__ tiles, int* __restrict__ cost_prefix, int nxb, int nyb, long long ntiles)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    cost_prefix[t] = (int)(16 * t);
+    if (t == ntiles) return;
+    K2Tile k;
+    k.xb = (int)(t % nxb);
+    k.yb = (int)((t / nxb) % nyb);
+    k.zb = (int)(t / ((long long)nxb * nyb));
+    k.pad_ = 0;
+    tiles[t] = k;
 }
 
 // ---- naive debug kernels (same tile lists, no tensor cores, no TMA) ------------------------------

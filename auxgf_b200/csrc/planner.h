@@ -27,15 +27,15 @@ struct SubTile { int i, j, a0, nb, bsel, esel, nv; long long col; double p, eij;
 
 inline int64_t rup(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// Column blocks (a0, nb) of one item of padded width w: ceil(w/64) blocks; `balanced` makes them nearly equal
-// (in units of 8 columns), e.g. 104 -> 56 + 48 rather than 64 + 40.
-inline std::vector<std::pair<int, int>> split_blocks(int64_t w, bool balanced) {
+// Column blocks (a0, nb) of one item of padded width w: ceil(w/64) blocks of 64 columns + the rest, e.g. 104 -> 64 + 40
+// (with the longest-first launch order this measured no worse than nearly equal blocks).
+inline std::vector<std::pair<int, int>> split_blocks(int64_t w) {
     std::vector<std::pair<int, int>> out;
     const int units = (int)(w / 8);
     const int nblk = (units + 7) / 8;
     int a0 = 0;
     for (int b = 0; b < nblk; ++b) {
-        int nb = balanced ? units / nblk + (b < units % nblk ? 1 : 0) : std::min(8, units - 8 * b);
+        const int nb = std::min(8, units - 8 * b);
         out.push_back({a0, nb});
         a0 += 8 * nb;
     }
@@ -80,7 +80,6 @@ struct PlanConfig {
     int num_sms = 148;
     bool simple = false;             // naive debug kernels: all-pairs route, no tuning, no thin tiles
     bool lpt_order = true;           // k1_form tiles of a chunk launched longest first
-    bool balanced_blocks = false;    // column blocks of an item of nearly equal width
     bool tune_chunk = true;          // chunk size chosen for whole waves of k1_form tiles
     bool thin_tiles = true;          // last x-block with <= 80 valid rows uses the thin-tile mapping
     bool coulomb = true;             // Coulomb factorisation allowed ...
@@ -178,8 +177,8 @@ struct MomentPlan {
         }
         sym_items.insert(sym_items.end(), diag_items.begin(), diag_items.end());
         sym_items.insert(sym_items.end(), os_items.begin(), os_items.end());
-        blk_same = split_blocks(vpad, cfg.balanced_blocks);
-        blk_other = split_blocks(vbpad, cfg.balanced_blocks);
+        blk_same = split_blocks(vpad);
+        blk_other = split_blocks(vbpad);
         for (int k = 0; k < 4; ++k) chunk_items[k] = 0;
         return 0;
     }

@@ -34,6 +34,14 @@ SYMBOLS = [
     "agf2_b200_set_simple_kernels", "agf2_b200_set_overlap", "agf2_b200_last_stage_ms",
     "agf2_b200_set_coulomb_factorization", "agf2_b200_last_plan", "agf2_b200_build_part_loop_rhf_sharded",
     "agf2_b200_build_part_loop_uhf_sharded", "agf2_b200_plan_stats",
+    # contexts, options, communicator (round 2)
+    "agf2_b200_ctx_create", "agf2_b200_ctx_destroy", "agf2_b200_ctx_get_device", "agf2_b200_ctx_synchronize",
+    "agf2_b200_ctx_set_option", "agf2_b200_set_deterministic", "agf2_b200_sticky_status",
+    "agf2_b200_ctx_last_stage_ms", "agf2_b200_ctx_last_plan", "agf2_b200_ctx_last_comm_bytes",
+    "agf2_b200_comm_get_unique_id", "agf2_b200_comm_init", "agf2_b200_comm_info", "agf2_b200_comm_allreduce",
+    "agf2_b200_comm_allgather", "agf2_b200_comm_broadcast", "agf2_b200_comm_barrier", "agf2_b200_comm_destroy",
+    "agf2_b200_ctx_moments_rhf_dev", "agf2_b200_ctx_moments_uhf_dev", "agf2_b200_ctx_build_part_loop_rhf",
+    "agf2_b200_ctx_build_part_loop_uhf", "agf2_b200_host_register", "agf2_b200_host_unregister",
 ]
 
 
@@ -78,6 +86,33 @@ _libagf2.agf2_b200_moments_uhf_dev.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, 
     [_dbl, _dbl, _i64, _i64, _vp, _vp, _vp, ctypes.c_int]
 _libagf2.agf2_b200_compress.argtypes = [_vp, _vp, _i64, _vp, _vp, ctypes.c_int]
 _libagf2.agf2_b200_eigh.argtypes = [_vp, _i64, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(_vp)]
+_libagf2.agf2_b200_ctx_destroy.argtypes = [_vp]
+_libagf2.agf2_b200_ctx_get_device.argtypes = [_vp, ctypes.POINTER(ctypes.c_int)]
+_libagf2.agf2_b200_ctx_synchronize.argtypes = [_vp]
+_libagf2.agf2_b200_ctx_set_option.argtypes = [_vp, ctypes.c_char_p, _i64]
+_libagf2.agf2_b200_set_deterministic.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_sticky_status.argtypes = [ctypes.c_int]
+_libagf2.agf2_b200_ctx_last_stage_ms.argtypes = [_vp, ctypes.POINTER(_dbl)]
+_libagf2.agf2_b200_ctx_last_plan.argtypes = [_vp, ctypes.POINTER(_i64)]
+_libagf2.agf2_b200_ctx_last_comm_bytes.argtypes = [_vp, ctypes.POINTER(_i64)]
+_libagf2.agf2_b200_comm_get_unique_id.argtypes = [_vp]
+_libagf2.agf2_b200_comm_init.argtypes = [_vp, _vp, ctypes.c_int, ctypes.c_int]
+_libagf2.agf2_b200_comm_info.argtypes = [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+_libagf2.agf2_b200_comm_allreduce.argtypes = [_vp, _vp, _i64, ctypes.c_int, _vp]
+_libagf2.agf2_b200_comm_allgather.argtypes = [_vp, _vp, _i64, _vp]
+_libagf2.agf2_b200_comm_broadcast.argtypes = [_vp, _vp, _i64, ctypes.c_int, _vp]
+_libagf2.agf2_b200_comm_barrier.argtypes = [_vp]
+_libagf2.agf2_b200_comm_destroy.argtypes = [_vp]
+_libagf2.agf2_b200_ctx_moments_rhf_dev.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp] + [_i64] * 6 + \
+    [_dbl, _dbl, _vp, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_ctx_moments_uhf_dev.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp] + \
+    [_i64] * 8 + [_dbl, _dbl, _vp, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_ctx_build_part_loop_rhf.argtypes = [_vp, _in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_ctx_build_part_loop_uhf.argtypes = [_vp, _in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_i64] * 8 + \
+    [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_host_register.argtypes = [_vp, _i64]
+_libagf2.agf2_b200_host_unregister.argtypes = [_vp]
 # the reference's own void symbols (drop-in ABI; argtypes as auxgf/lib/agf2.py:28-60)
 _u32 = ctypes.c_uint32
 _libagf2.build_part_loop_rhf.restype = None
@@ -151,6 +186,75 @@ def set_overlap(on):
 
 def set_workspace_bytes(nbytes):
     check(_libagf2.agf2_b200_set_workspace_bytes(int(nbytes)))
+
+
+def set_device(index):
+    """Make GPU ``index`` the calling thread's current device (the library's default context follows it)."""
+    check(_libagf2.agf2_b200_set_device(int(index)))
+
+
+def set_deterministic(on):
+    """Stream-K partial tiles summed in a fixed order (default on): the same build gives the same bits."""
+    check(_libagf2.agf2_b200_set_deterministic(1 if on else 0))
+
+
+def set_option(name, value, ctx=None):
+    check(_libagf2.agf2_b200_ctx_set_option(ctx, name.encode(), int(value)))
+
+
+def sticky_status(clear=False):
+    """(status, message) of the first failure of a ``void`` drop-in call (they cannot return one); 0 = none."""
+    st = int(_libagf2.agf2_b200_sticky_status(1 if clear else 0))
+    return st, (_libagf2.agf2_b200_last_error().decode() if st else "")
+
+
+def last_comm_bytes(ctx=None):
+    """Bytes this rank sent over NVLink in the last communicator-aware call: (all-gather, all-reduce)."""
+    out = (_i64 * 2)()
+    check(_libagf2.agf2_b200_ctx_last_comm_bytes(ctx, out))
+    return int(out[0]), int(out[1])
+
+
+# ---- communicator of the default context (one rank per process / GPU; NCCL inside the library) ----
+def comm_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    check(_libagf2.agf2_b200_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(uid, rank, size, ctx=None):
+    assert len(uid) == 128
+    check(_libagf2.agf2_b200_comm_init(ctx, ctypes.create_string_buffer(uid, 128), int(rank), int(size)))
+
+
+def comm_info(ctx=None):
+    r, n = ctypes.c_int(0), ctypes.c_int(1)
+    check(_libagf2.agf2_b200_comm_info(ctx, ctypes.byref(r), ctypes.byref(n)))
+    return r.value, n.value
+
+
+def comm_barrier(ctx=None):
+    check(_libagf2.agf2_b200_comm_barrier(ctx))
+
+
+def comm_destroy(ctx=None):
+    check(_libagf2.agf2_b200_comm_destroy(ctx))
+
+
+def comm_allreduce(m, op="sum", ctx=None):
+    """Sum (max / min) over the ranks of the communicator.  CUDA f64 tensors: in place, asynchronous on the current
+    torch stream.  NumPy arrays: staged through the GPU, returns the reduced array."""
+    import torch
+    opc = {"sum": 0, "max": 1, "min": 2}[op]
+    if isinstance(m, torch.Tensor):
+        _check_dev(m, "tensor")
+        check(_libagf2.agf2_b200_comm_allreduce(ctx, m.data_ptr(), m.numel(), opc,
+                                                torch.cuda.current_stream(m.device).cuda_stream))
+        return m
+    a = np.ascontiguousarray(m, dtype=_f64)
+    t = torch.from_numpy(a).cuda()
+    check(_libagf2.agf2_b200_comm_allreduce(ctx, t.data_ptr(), t.numel(), opc, torch.cuda.current_stream().cuda_stream))
+    return t.cpu().numpy().reshape(a.shape)
 
 
 def _c(a, ndim):
@@ -266,10 +370,13 @@ def _check_dev(t, name):
 
 
 def moments_rhf_dev(ixq, qja, ei, ea, istart=0, iend=None, os_factor=1.0, ss_factor=1.0, part=0, nparts=1,
-                    vv=None, vev=None, sync=True, naux=None):
+                    vv=None, vev=None, sync=True, naux=None, comm=False, ei_host=None):
     """Device-resident moment build.  ixq: (nocc, nphys, ld>=naux), qja: (naux, nocc, ld>=nvir) CUDA f64
     tensors whose last dimension may be padded to an even pitch (logical sizes: ``naux`` keyword,
-    ``ea.numel()``).  Returns (vv, vev) CUDA tensors (accumulated into when given)."""
+    ``ea.numel()``).  Returns (vv, vev) CUDA tensors (accumulated into when given).
+    ``comm=True``: this rank's share of the pair-work items (rank / size of the library's communicator) followed by
+    ONE NCCL all-reduce of the packed [vv|vev] inside the library, on the same stream.  ``ei_host``: NumPy copy of
+    ``ei`` (saves the library a device->host copy and a stream synchronisation)."""
     import torch
     _check_dev(ixq, "ixq"); _check_dev(qja, "qja"); _check_dev(ei, "ei"); _check_dev(ea, "ea")
     nocc, nphys, ld_ixq = ixq.shape
@@ -283,15 +390,22 @@ def moments_rhf_dev(ixq, qja, ei, ea, istart=0, iend=None, os_factor=1.0, ss_fac
     if vev is None:
         vev = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq.device)
     stream = torch.cuda.current_stream(ixq.device).cuda_stream
-    check(_libagf2.agf2_b200_moments_rhf_dev(ixq.data_ptr(), ld_ixq, qja.data_ptr(), ld_qja, ei.data_ptr(),
-                                             ea.data_ptr(), nphys, nocc, nvir, naux, istart, iend, os_factor,
-                                             ss_factor, part, nparts, vv.data_ptr(), vev.data_ptr(), stream,
-                                             1 if sync else 0))
+    if comm:
+        eh = None if ei_host is None else _c(ei_host, 1)
+        check(_libagf2.agf2_b200_ctx_moments_rhf_dev(None, ixq.data_ptr(), ld_ixq, qja.data_ptr(), ld_qja,
+                                                     ei.data_ptr(), ea.data_ptr(), None if eh is None else eh.ctypes.data,
+                                                     nphys, nocc, nvir, naux, istart, iend, os_factor, ss_factor,
+                                                     vv.data_ptr(), vev.data_ptr(), stream, 1 if sync else 0))
+    else:
+        check(_libagf2.agf2_b200_moments_rhf_dev(ixq.data_ptr(), ld_ixq, qja.data_ptr(), ld_qja, ei.data_ptr(),
+                                                 ea.data_ptr(), nphys, nocc, nvir, naux, istart, iend, os_factor,
+                                                 ss_factor, part, nparts, vv.data_ptr(), vev.data_ptr(), stream,
+                                                 1 if sync else 0))
     return vv, vev
 
 
 def moments_uhf_dev(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, istart=0, iend=None, os_factor=1.0,
-                    ss_factor=1.0, part=0, nparts=1, vv=None, vev=None, sync=True, naux=None):
+                    ss_factor=1.0, part=0, nparts=1, vv=None, vev=None, sync=True, naux=None, comm=False):
     import torch
     for t, n in ((ixq_a, "ixq_a"), (qja_a, "qja_a"), (qja_b, "qja_b"), (ei_a, "ei_a"), (ei_b, "ei_b"),
                  (ea_a, "ea_a"), (ea_b, "ea_b")):
@@ -305,76 +419,59 @@ def moments_uhf_dev(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, istart=0, iend=
     if vev is None:
         vev = torch.zeros((nphys, nphys), dtype=torch.float64, device=ixq_a.device)
     stream = torch.cuda.current_stream(ixq_a.device).cuda_stream
-    check(_libagf2.agf2_b200_moments_uhf_dev(ixq_a.data_ptr(), ld_ixq, qja_a.data_ptr(), qja_a.shape[2],
-                                             qja_b.data_ptr(), qja_b.shape[2], ei_a.data_ptr(), ei_b.data_ptr(),
-                                             ea_a.data_ptr(), ea_b.data_ptr(), nphys, nocc_a, nocc_b, nvir_a,
-                                             nvir_b, naux, istart, iend, os_factor, ss_factor, part, nparts,
-                                             vv.data_ptr(), vev.data_ptr(), stream, 1 if sync else 0))
+    if comm:
+        check(_libagf2.agf2_b200_ctx_moments_uhf_dev(None, ixq_a.data_ptr(), ld_ixq, qja_a.data_ptr(), qja_a.shape[2],
+                                                     qja_b.data_ptr(), qja_b.shape[2], ei_a.data_ptr(), ei_b.data_ptr(),
+                                                     ea_a.data_ptr(), ea_b.data_ptr(), None, None, nphys, nocc_a, nocc_b,
+                                                     nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor,
+                                                     vv.data_ptr(), vev.data_ptr(), stream, 1 if sync else 0))
+    else:
+        check(_libagf2.agf2_b200_moments_uhf_dev(ixq_a.data_ptr(), ld_ixq, qja_a.data_ptr(), qja_a.shape[2],
+                                                 qja_b.data_ptr(), qja_b.shape[2], ei_a.data_ptr(), ei_b.data_ptr(),
+                                                 ea_a.data_ptr(), ea_b.data_ptr(), nphys, nocc_a, nocc_b, nvir_a,
+                                                 nvir_b, naux, istart, iend, os_factor, ss_factor, part, nparts,
+                                                 vv.data_ptr(), vev.data_ptr(), stream, 1 if sync else 0))
     return vv, vev
-
-
-def moments_rhf_gathered(ixq, qja, ei, ea, nphys, os_factor=1.0, ss_factor=1.0):
-    """Host arrays in, host (vv, vev) out, on every rank of a torch.distributed (NCCL) job -- the multi-GPU
-    counterpart of ``moments_rhf``.  Instead of every rank pulling the whole of ``ixq``/``qja`` over PCIe (what the
-    reference's replicated MPI ranks imply, auxgf/mpi/agf2/optragf2.py:370-395), rank r uploads poles
-    [o r/W, o (r+1)/W) of ``ixq`` and rows [N r/W, N (r+1)/W) of ``qja``, the GPUs all-gather them over NVLink,
-    each builds its share of the pair-work items (part/nparts) and ONE all-reduce sums [vv|vev]."""
-    import torch
-    import torch.distributed as dist
-    rank, world = dist.get_rank(), dist.get_world_size()
-    dev = torch.device("cuda", torch.cuda.current_device())
-    ei = _c(ei, 1); ea = _c(ea, 1)
-    nocc, nvir = ei.size, ea.size
-    ixq = np.asarray(ixq).reshape(nocc, nphys, -1)
-    naux = ixq.shape[2]
-    qja = np.asarray(qja).reshape(naux, nocc, nvir)
-    ldn, ldv = naux + (naux & 1), nvir + (nvir & 1)              # even pitches (16-byte TMA strides)
-
-    def gather(host, n0, tail_shape, ld):
-        per = (n0 + world - 1) // world
-        full = torch.empty((world * per,) + tail_shape[:-1] + (ld,), dtype=torch.float64, device=dev)
-        lo, hi = min(n0, rank * per), min(n0, (rank + 1) * per)
-        mine = full[rank * per:(rank + 1) * per]
-        if ld != tail_shape[-1]:
-            mine.zero_()
-        if hi > lo:
-            mine[:hi - lo, ..., :tail_shape[-1]].copy_(torch.from_numpy(host[lo:hi]), non_blocking=False)
-        dist.all_gather_into_tensor(full, mine.clone() if world > 1 else mine)
-        return full[:n0]
-
-    d_ixq = gather(ixq, nocc, (nphys, naux), ldn)
-    d_qja = gather(qja, naux, (nocc, nvir), ldv)
-    d_ei = torch.from_numpy(ei).to(dev); d_ea = torch.from_numpy(ea).to(dev)
-    out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
-    moments_rhf_dev(d_ixq, d_qja, d_ei, d_ea, os_factor=os_factor, ss_factor=ss_factor, part=rank, nparts=world,
-                    vv=out[0], vev=out[1], sync=False, naux=naux)
-    dist.all_reduce(out)
-    h = out.cpu().numpy()
-    return h[0], h[1]
 
 
 def moments_rhf_multi(ixq, qja, ei, ea, nphys, os_factor=1.0, ss_factor=1.0):
-    """Host arrays in, host (vv, vev) out, summed over the ranks of a torch.distributed job (one process per GPU).
-    Two ways to get the inputs into HBM: (a) every rank streams the whole of ixq through the C host-pointer ABI, pole
-    by pole under its share of the pair loop -- free while the upload is shorter than the rank's compute; (b)
-    ``moments_rhf_gathered``: every rank uploads 1/world of the inputs and NVLink does the rest.  Picks (a) unless
-    the estimated upload (pageable host memory, ~8 GB/s) would outlast the rank's compute (~40 TFLOP/s)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    nocc, nvir = np.size(ei), np.size(ea)
-    naux = np.asarray(ixq).size // (nocc * nphys)
-    t_upload = 8.0 * nocc * nphys * naux / 8e9
-    t_compute = (2.0 * nphys * naux + 4.0 * nphys * nphys) * nocc * nocc * nvir / (40e12 * world)
-    if world > 1 and t_upload > 0.9 * t_compute:
-        return moments_rhf_gathered(ixq, qja, ei, ea, nphys, os_factor, ss_factor)
-    vv, vev = moments_rhf(ixq, qja, ei, ea, nphys, os_factor=os_factor, ss_factor=ss_factor, part=rank, nparts=world)
-    if world > 1:
-        buf = torch.from_numpy(np.stack([vv, vev])).cuda()
-        dist.all_reduce(buf)
-        vv, vev = buf.cpu().numpy()
+    """Host arrays in, host (vv, vev) out, on every rank of the library's communicator (one process per GPU) -- the
+    multi-GPU counterpart of ``moments_rhf`` and the call that replaces the replicated MPI ranks + Reduce/Bcast of
+    auxgf/mpi/agf2/optragf2.py:370-395.  Everything happens inside ``agf2_b200_ctx_build_part_loop_rhf``: rank r copies
+    1/N of ``ixq`` and ``qja`` over PCIe, in groups pipelined under the pair loop; the GPUs all-gather the groups over
+    NVLink; each builds its share of the pair-work items; ONE all-reduce sums the packed [vv|vev]."""
+    ei = _c(ei, 1); ea = _c(ea, 1)
+    nocc, nvir = ei.size, ea.size
+    ixq = _c(np.asarray(ixq).reshape(nocc * nphys, -1), 2)
+    naux = ixq.shape[1]
+    qja = _c(np.asarray(qja).reshape(naux, nocc * nvir), 2)
+    vv = np.zeros((nphys, nphys)); vev = np.zeros((nphys, nphys))
+    check(_libagf2.agf2_b200_ctx_build_part_loop_rhf(None, ixq, qja, ei, ea, nphys, nocc, nvir, naux, 0, nocc,
+                                                     os_factor, ss_factor, vv, vev))
     return vv, vev
+
+
+def moments_uhf_multi(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, os_factor=1.0, ss_factor=1.0):
+    """UHF channel counterpart of ``moments_rhf_multi`` (``agf2_b200_ctx_build_part_loop_uhf``)."""
+    ei_a = _c(ei_a, 1); ei_b = _c(ei_b, 1); ea_a = _c(ea_a, 1); ea_b = _c(ea_b, 1)
+    oa, ob, va, vb = ei_a.size, ei_b.size, ea_a.size, ea_b.size
+    ixq_a = _c(np.asarray(ixq_a).reshape(oa * nphys, -1), 2)
+    naux = ixq_a.shape[1]
+    qja_a = _c(np.asarray(qja_a).reshape(naux, oa * va), 2)
+    qja_b = _c(np.asarray(qja_b).reshape(naux, ob * vb), 2)
+    vv = np.zeros((nphys, nphys)); vev = np.zeros((nphys, nphys))
+    check(_libagf2.agf2_b200_ctx_build_part_loop_uhf(None, ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, oa, ob,
+                                                     va, vb, naux, 0, oa, os_factor, ss_factor, vv, vev))
+    return vv, vev
+
+
+def host_register(a):
+    """Page-lock a NumPy array so that the host-pointer calls upload it by asynchronous DMA (optional)."""
+    check(_libagf2.agf2_b200_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a):
+    check(_libagf2.agf2_b200_host_unregister(a.ctypes.data))
 
 
 def compress_dev(vv, vev):
@@ -471,18 +568,28 @@ class DeviceERI:
         _check2(_libagf2.agf2_b200_get_jk(self._h, rdm1.ctypes.data, j.ctypes.data, k.ctypes.data, 0, self._stream()))
         return j, k
 
-    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
-        """vv, vev (CUDA tensors) of one sector, everything on the device."""
+    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=None, nparts=None):
+        """Packed [vv|vev] (CUDA tensor) of one sector, everything on the device.  By default the work is shared over
+        the ranks of the library's communicator and summed with one all-reduce inside the library; explicit
+        ``part``/``nparts`` return this part's contribution only."""
         import torch
+        use_comm = part is None
+        part, nparts = (0, 1) if part is None else (part, nparts)
         dev = torch.device("cuda", torch.cuda.current_device())
         nphys, nocc, nvir = self.nphys, gf_occ.naux, gf_vir.naux
         ixq, ldi, qja, ldq = self.sector(gf_occ.v, gf_vir.v)
         ei = torch.from_numpy(_c(gf_occ.e, 1)).to(dev)
         ea = torch.from_numpy(_c(gf_vir.e, 1)).to(dev)
         out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
-        check(_libagf2.agf2_b200_moments_rhf_dev(ixq, ldi, qja, ldq, ei.data_ptr(), ea.data_ptr(), nphys, nocc,
-                                                 nvir, self.naux, 0, nocc, os_factor, ss_factor, part, nparts,
-                                                 out[0].data_ptr(), out[1].data_ptr(), self._stream(), 1))
+        if use_comm:
+            check(_libagf2.agf2_b200_ctx_moments_rhf_dev(None, ixq, ldi, qja, ldq, ei.data_ptr(), ea.data_ptr(),
+                                                         _c(gf_occ.e, 1).ctypes.data, nphys, nocc, nvir, self.naux, 0,
+                                                         nocc, os_factor, ss_factor, out[0].data_ptr(),
+                                                         out[1].data_ptr(), self._stream(), 1))
+        else:
+            check(_libagf2.agf2_b200_moments_rhf_dev(ixq, ldi, qja, ldq, ei.data_ptr(), ea.data_ptr(), nphys, nocc,
+                                                     nvir, self.naux, 0, nocc, os_factor, ss_factor, part, nparts,
+                                                     out[0].data_ptr(), out[1].data_ptr(), self._stream(), 1))
         return out
 
     @staticmethod
@@ -492,9 +599,15 @@ class DeviceERI:
         return e.cpu().numpy(), c.cpu().numpy()
 
     @staticmethod
-    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
-        """One spin channel of OptUAGF2.build_part: eri_a/gf_*[0] same spin, eri_b/gf_*[1] opposite spin."""
+    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=None, nparts=None):
+        """One spin channel of OptUAGF2.build_part: eri_a/gf_*[0] same spin, eri_b/gf_*[1] opposite spin.
+        ``part``/``nparts`` as in ``moments_rhf``."""
         import torch
+        if eri_a is eri_b:
+            raise ValueError("moments_uhf needs one staged DeviceERI per spin: sector() scratch of a handle is "
+                             "overwritten by its next sector() call")
+        use_comm = part is None
+        part, nparts = (0, 1) if part is None else (part, nparts)
         dev = torch.device("cuda", torch.cuda.current_device())
         nphys = eri_a.nphys
         ixq, ldi, qja, ldq = eri_a.sector(gf_occ[0].v, gf_vir[0].v)
@@ -502,9 +615,18 @@ class DeviceERI:
         T = lambda a: torch.from_numpy(_c(a, 1)).to(dev)  # noqa: E731
         eia, eib, eaa, eab = T(gf_occ[0].e), T(gf_occ[1].e), T(gf_vir[0].e), T(gf_vir[1].e)
         out = torch.zeros((2, nphys, nphys), dtype=torch.float64, device=dev)
-        check(_libagf2.agf2_b200_moments_uhf_dev(ixq, ldi, qja, ldq, qjb, ldqb, eia.data_ptr(), eib.data_ptr(),
-                                                 eaa.data_ptr(), eab.data_ptr(), nphys, gf_occ[0].naux,
-                                                 gf_occ[1].naux, gf_vir[0].naux, gf_vir[1].naux, eri_a.naux, 0,
-                                                 gf_occ[0].naux, os_factor, ss_factor, part, nparts,
-                                                 out[0].data_ptr(), out[1].data_ptr(), eri_a._stream(), 1))
+        if use_comm:
+            check(_libagf2.agf2_b200_ctx_moments_uhf_dev(None, ixq, ldi, qja, ldq, qjb, ldqb, eia.data_ptr(),
+                                                         eib.data_ptr(), eaa.data_ptr(), eab.data_ptr(),
+                                                         _c(gf_occ[0].e, 1).ctypes.data, _c(gf_occ[1].e, 1).ctypes.data,
+                                                         nphys, gf_occ[0].naux, gf_occ[1].naux, gf_vir[0].naux,
+                                                         gf_vir[1].naux, eri_a.naux, 0, gf_occ[0].naux, os_factor,
+                                                         ss_factor, out[0].data_ptr(), out[1].data_ptr(),
+                                                         eri_a._stream(), 1))
+        else:
+            check(_libagf2.agf2_b200_moments_uhf_dev(ixq, ldi, qja, ldq, qjb, ldqb, eia.data_ptr(), eib.data_ptr(),
+                                                     eaa.data_ptr(), eab.data_ptr(), nphys, gf_occ[0].naux,
+                                                     gf_occ[1].naux, gf_vir[0].naux, gf_vir[1].naux, eri_a.naux, 0,
+                                                     gf_occ[0].naux, os_factor, ss_factor, part, nparts,
+                                                     out[0].data_ptr(), out[1].data_ptr(), eri_a._stream(), 1))
         return out

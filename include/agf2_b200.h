@@ -10,8 +10,11 @@
  *      library in place of agf2.so without touching auxgf/lib/agf2.py:
  *          build_part_loop_rhf   replaces  auxgf/lib/libagf2/optragf2.c:32-43
  *          build_part_loop_uhf   replaces  auxgf/lib/libagf2/optuagf2.c:31-47
- *      They return void like the reference; a failure (no CUDA device, CUDA error) prints the
- *      message to stderr and aborts -- there is NO CPU fallback.
+ *      They return void like the reference and there is NO CPU fallback: a failure (no CUDA device,
+ *      CUDA error) leaves vv/vev untouched, prints the message to stderr and records a sticky status
+ *      that agf2_b200_sticky_status() / agf2_b200_last_error() return (the caller then fails on the
+ *      Cholesky of a zero vv, as the reference does on any non-SPD vv).  Set the environment variable
+ *      AGF2_B200_ABORT_ON_ERROR=1 to abort() the process instead.
  *
  *  (2) STATUS-RETURNING entry points (`agf2_b200_*`): same arithmetic, 64-bit sizes, explicit
  *      SCS factors, device-resident variants (inputs already in HBM, no host<->device copies),
@@ -19,8 +22,18 @@
  *      cholesky/inv/eigh of auxgf/agf2/optragf2.py:270-278) and a dense symmetric eigensolver for
  *      the extended Fock matrix (replaces np.linalg.eigh in auxgf/aux/eig.py:23-33).
  *      Return value: 0 on success, an AGF2_B200_E* code otherwise; agf2_b200_last_error() gives
- *      the text.  All calls are made from one host thread per device context; the library owns its
- *      CUDA streams and scratch memory.
+ *      the text (per calling thread).
+ *
+ *  (3) CONTEXTS and the COMMUNICATOR.  An agf2_b200_ctx owns the CUDA streams, scratch memory,
+ *      instrumentation and -- optionally -- one rank of an NCCL communicator (one context per GPU;
+ *      NCCL is loaded at run time, the library does not link it).  Several contexts per process are
+ *      fine (one per device, or more); calls on one context are serialised by the library.  The
+ *      entry points without a ctx argument use the DEFAULT context of the calling thread's current
+ *      CUDA device (created on first use); pass NULL for `ctx` to name it explicitly.  Replaces the
+ *      OpenMP team + mpi4py communicator of the reference (optragf2.c:95-115, auxgf/util/mpi.py:25-69).
+ *      Threading contract: any thread may call; a context is used by one call at a time; scratch
+ *      buffers are shared between calls of a context, so asynchronous device calls (sync = 0) on one
+ *      context must all be given the same stream.
  *
  * Array conventions (identical to the reference, auxgf/lib/agf2.py:63-145):
  *      ixq   (nocc*nphys, naux)   row-major f64,  element [(i, x), Q]     = (i x | Q)
@@ -49,7 +62,8 @@ enum {
     AGF2_B200_EINVAL = 3,    /* bad argument (sizes, alignment, null pointer) */
     AGF2_B200_ENOMEM = 4,    /* device allocation failed */
     AGF2_B200_ENOTSPD = 5,   /* vv is not positive definite (Cholesky failed; reference raises LinAlgError) */
-    AGF2_B200_ESOLVER = 6    /* cuSOLVER / cuBLAS failure */
+    AGF2_B200_ESOLVER = 6,   /* cuSOLVER / cuBLAS failure */
+    AGF2_B200_ECOMM = 7      /* NCCL failure / no communicator */
 };
 
 /* ---- (1) drop-in symbols: reference signatures, host memory -------------------------------- */
@@ -71,8 +85,88 @@ void build_part_loop_uhf(double *ixq_a, double *qja_a, double *qja_b,
 const char *agf2_b200_last_error(void);
 const char *agf2_b200_version(void);
 
-/* Select the CUDA device this thread's context uses (default: current device). */
+/* First failure of a void drop-in call since the last clear (0 = none); agf2_b200_last_error() then
+ * returns its text.  clear != 0 resets it. */
+int agf2_b200_sticky_status(int clear);
+
+/* cudaSetDevice for the calling thread: the entry points without a ctx argument then use that
+ * device's default context. */
 int agf2_b200_set_device(int device);
+
+/* ---- (3) contexts ------------------------------------------------------------------------------ */
+typedef struct agf2_b200_ctx agf2_b200_ctx;
+
+/* A new context on `device` (< 0: the current device) with its own streams, scratch and options
+ * (initialised from the process defaults). */
+int agf2_b200_ctx_create(int device, agf2_b200_ctx **out);
+int agf2_b200_ctx_destroy(agf2_b200_ctx *ctx);
+int agf2_b200_ctx_get_device(agf2_b200_ctx *ctx, int *device);
+int agf2_b200_ctx_synchronize(agf2_b200_ctx *ctx);
+
+/* Options by name: "workspace_bytes", "overlap", "deterministic", "coulomb_factorization" (0/1/2),
+ * "simple_kernels", "thin_tiles", "lpt_order", "tune_chunk", "profile".  ctx == NULL: the process
+ * defaults, which the default contexts of all devices share. */
+int agf2_b200_ctx_set_option(agf2_b200_ctx *ctx, const char *name, int64_t value);
+
+/* Instrumentation of the last moments call on a context (NULL: default context): see the variants
+ * without ctx below; comm bytes = what this rank sent over NVLink: [0] all-gather, [1] all-reduce. */
+int agf2_b200_ctx_last_stage_ms(agf2_b200_ctx *ctx, double *ms4);
+int agf2_b200_ctx_last_plan(agf2_b200_ctx *ctx, int64_t *info6);
+int agf2_b200_ctx_last_comm_bytes(agf2_b200_ctx *ctx, int64_t *bytes2);
+
+/* ---- communicator: one rank per context, NCCL over NVLink / NVSwitch -------------------------------
+ * Replaces comm.Reduce + comm.Bcast of auxgf/util/mpi.py:60-64 (auxgf/mpi/agf2/optragf2.py:394-395).
+ * Rank 0 obtains the 128-byte id, the caller distributes it (file, socket, launcher env ...), every
+ * rank calls comm_init (collective).  No MPI is involved. */
+int agf2_b200_comm_get_unique_id(void *id128);
+int agf2_b200_comm_init(agf2_b200_ctx *ctx, const void *id128, int rank, int nranks);
+int agf2_b200_comm_info(agf2_b200_ctx *ctx, int *rank, int *nranks);
+/* in-place collectives on DEVICE f64 buffers, asynchronous on `stream`; op: 0 sum, 1 max, 2 min;
+ * all-gather: rank r's piece is buf[r * count_per_rank ...]. */
+int agf2_b200_comm_allreduce(agf2_b200_ctx *ctx, double *buf, int64_t count, int op, void *stream);
+int agf2_b200_comm_allgather(agf2_b200_ctx *ctx, double *buf, int64_t count_per_rank, void *stream);
+int agf2_b200_comm_broadcast(agf2_b200_ctx *ctx, double *buf, int64_t count, int root, void *stream);
+/* every rank has arrived and the device is idle */
+int agf2_b200_comm_barrier(agf2_b200_ctx *ctx);
+int agf2_b200_comm_destroy(agf2_b200_ctx *ctx);
+
+/* Moment build on a context with a communicator: this rank builds the pair-work items
+ * [rank, nranks) and ONE ncclAllReduce(sum, f64) of the packed [vv | vev] follows k3_finalize on the
+ * same stream; every rank ends up with the full result added into its vv/vev.  Without a communicator:
+ * identical to the plain device-resident calls.  ei_host (may be NULL): host copy of the pole energies
+ * -- saves a device->host copy and a stream synchronisation at the start of the call. */
+int agf2_b200_ctx_moments_rhf_dev(agf2_b200_ctx *ctx, const double *ixq, int64_t ld_ixq, const double *qja,
+                                  int64_t ld_qja, const double *ei, const double *ea, const double *ei_host,
+                                  int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, int64_t istart,
+                                  int64_t iend, double os_factor, double ss_factor, double *vv, double *vev,
+                                  void *stream, int sync);
+int agf2_b200_ctx_moments_uhf_dev(agf2_b200_ctx *ctx, const double *ixq_a, int64_t ld_ixq, const double *qja_a,
+                                  int64_t ld_qja_a, const double *qja_b, int64_t ld_qja_b, const double *ei_a,
+                                  const double *ei_b, const double *ea_a, const double *ea_b,
+                                  const double *ei_a_host, const double *ei_b_host, int64_t nphys,
+                                  int64_t nocc_a, int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
+                                  int64_t istart, int64_t iend, double os_factor, double ss_factor, double *vv,
+                                  double *vev, void *stream, int sync);
+
+/* Host-pointer build on a context with a communicator -- the multi-GPU form of the drop-in call: every
+ * rank passes the same host arrays; rank r copies 1/N of ixq (groups of poles, pipelined under the
+ * pair loop) and of qja over PCIe, NCCL all-gathers replicate them over NVLink, the ranks build their
+ * shares, one all-reduce, and every rank adds the full result into its host vv/vev. */
+int agf2_b200_ctx_build_part_loop_rhf(agf2_b200_ctx *ctx, const double *ixq, const double *qja,
+                                      const double *ei, const double *ea, int64_t nphys, int64_t nocc,
+                                      int64_t nvir, int64_t naux, int64_t istart, int64_t iend,
+                                      double os_factor, double ss_factor, double *vv, double *vev);
+int agf2_b200_ctx_build_part_loop_uhf(agf2_b200_ctx *ctx, const double *ixq_a, const double *qja_a,
+                                      const double *qja_b, const double *ei_a, const double *ei_b,
+                                      const double *ea_a, const double *ea_b, int64_t nphys, int64_t nocc_a,
+                                      int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
+                                      int64_t istart, int64_t iend, double os_factor, double ss_factor,
+                                      double *vv, double *vev);
+
+/* Optional: page-lock a caller-owned host buffer (cudaHostRegister) so that the uploads of the
+ * host-pointer calls are asynchronous DMA transfers; pageable memory works too. */
+int agf2_b200_host_register(const void *ptr, int64_t bytes);
+int agf2_b200_host_unregister(const void *ptr);
 
 /* Workspace for the (xi|ja) chunk that flows between the two kernels, in bytes per buffer
  * (two buffers are kept).  Default 40 MiB each so that both stay resident in the 126 MB L2. */
@@ -202,6 +296,11 @@ int agf2_b200_set_coulomb_factorization(int mode);
 /* Chunks alternate between two CUDA streams (default on) so that the tail of one kernel is filled by the
  * other chain's CTAs.  Switch it off to time k1_form / k2_moment in isolation (agf2_b200_last_kernel_ms). */
 int agf2_b200_set_overlap(int on);
+
+/* Stream-K partial tiles of k2_moment are summed in a fixed order (default on): repeating a build
+ * gives bit-identical moments.  Off: partial tiles go straight into the accumulators with
+ * red.global.add.f64 (order not fixed, results equal to ~1e-15 relative). */
+int agf2_b200_set_deterministic(int on);
 
 /* Debug: route the moment build through the naive one-thread-per-element CUDA kernels (same
  * planner, no tensor cores); used by the tests to separate planner bugs from kernel bugs. */

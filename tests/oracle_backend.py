@@ -3,6 +3,7 @@ the host-side driver logic (Aux, Fock loop, energies, multi-rank sharding) can b
 GPU, and so that GPU runs can be compared driver-to-driver.  Never imported by the package."""
 import numpy as np
 
+from auxgf_b200.util import mpi
 from oracle import agf2_oracle as orc
 
 
@@ -28,18 +29,20 @@ class _HostERI:
         k = np.einsum("Qpr,rs,Qqs->pq", self.full, rdm1, self.full, optimize=True)
         return j, k
 
-    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+    def moments_rhf(self, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0):
         o, v, p = gf_occ.naux, gf_vir.naux, self.nphys
+        part, nparts = mpi.rank(), mpi.size()
         ixq, qja = self._blocks(gf_occ.v, gf_vir.v)
         # the oracle shards by contiguous pole slices (auxgf/mpi/agf2/optragf2.py:370-374)
         lo, hi = (o * part) // nparts, (o * (part + 1)) // nparts
         vv, vev = orc.np_build_part_loop_rhf(ixq.reshape(o * p, -1), qja.reshape(self.naux, -1), gf_occ.e, gf_vir.e,
                                              p, o, v, self.naux, lo, hi, os_factor, ss_factor)
-        return _Packed(np.stack([vv, vev]))
+        return _Packed(mpi.reduce(np.stack([vv, vev])))
 
     @staticmethod
-    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0, part=0, nparts=1):
+    def moments_uhf(eri_a, eri_b, gf_occ, gf_vir, os_factor=1.0, ss_factor=1.0):
         p = eri_a.nphys
+        part, nparts = mpi.rank(), mpi.size()
         oa, ob, va, vb = gf_occ[0].naux, gf_occ[1].naux, gf_vir[0].naux, gf_vir[1].naux
         ixq_a, qja_a = eri_a._blocks(gf_occ[0].v, gf_vir[0].v)
         _, qja_b = eri_b._blocks(gf_occ[1].v, gf_vir[1].v)
@@ -47,7 +50,7 @@ class _HostERI:
         vv, vev = orc.np_build_part_loop_uhf(ixq_a.reshape(oa * p, -1), qja_a.reshape(eri_a.naux, -1),
                                              qja_b.reshape(eri_a.naux, -1), gf_occ[0].e, gf_occ[1].e, gf_vir[0].e,
                                              gf_vir[1].e, p, oa, ob, va, vb, eri_a.naux, lo, hi, os_factor, ss_factor)
-        return _Packed(np.stack([vv, vev]))
+        return _Packed(mpi.reduce(np.stack([vv, vev])))
 
     @staticmethod
     def compress(mom):
@@ -55,7 +58,7 @@ class _HostERI:
 
 
 class _Packed:
-    """Host stand-in for the packed [vv|vev] CUDA tensor; all-reduced through torch.distributed (gloo)."""
+    """Host stand-in for the packed [vv|vev] CUDA tensor (summed over the ranks through auxgf_b200.util.mpi)."""
     def __init__(self, a):
         self.a = a
 

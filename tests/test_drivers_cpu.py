@@ -155,6 +155,24 @@ def test_energy_functions_match_reference_loops():
     assert abs(energy.energy_mp2_aux(mo, se) - ref) < 1e-12
 
 
+class _GlooComm:
+    """TEST-ONLY communicator (torch.distributed over gloo on CPU) with the interface of auxgf_b200.util.mpi."""
+
+    def __init__(self, rank, size):
+        self.rank, self.size = rank, size
+
+    def reduce(self, m):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(m, dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def barrier(self):
+        import torch.distributed as dist
+        dist.barrier()
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -164,7 +182,9 @@ def _worker(rank, world, port, q):
     from oracle_backend import OracleBackend as OB
     from auxgf_b200 import backend as be
     from auxgf_b200.agf2 import OptRAGF2
+    from auxgf_b200.util import mpi
     be.use(OB())
+    mpi.use(_GlooComm(rank, world))
     hf = ModelRHF(nao=8, nocc=3, naux=20, seed=6).run()
     g = OptRAGF2(hf, verbose=False)
     g.options["maxiter"] = 2
