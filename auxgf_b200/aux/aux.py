@@ -41,14 +41,19 @@ class Aux:
                    chempot=self.chempot)
 
     def save(self, filename):
+        """Checkpoint in the reference's format: a pickle of the instance dict, keys ``_ener``, ``_coup``,
+        ``chempot`` (aux.py:735-741), so that either code restarts from the other's ``se_chk.pickle``."""
         with open(filename, "wb") as f:
-            pickle.dump({"e": self._ener, "v": self._coup, "chempot": self.chempot}, f)
+            pickle.dump({"_ener": self._ener, "_coup": self._coup, "chempot": self.chempot}, f)
 
     @classmethod
     def load(cls, filename):
+        """Reads the reference's checkpoints (aux.py:744-761) and the ``e``/``v`` keyed ones of earlier versions."""
         with open(filename, "rb") as f:
             d = pickle.load(f)
-        return cls(d["e"], d["v"], chempot=d["chempot"])
+        e = d["_ener"] if "_ener" in d else d["e"]
+        v = d["_coup"] if "_coup" in d else d["v"]
+        return cls(e, v, chempot=d.get("chempot", 0.0))
 
     # ---- views ---------------------------------------------------------------------------
     def as_occupied(self):

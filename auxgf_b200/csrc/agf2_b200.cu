@@ -250,6 +250,9 @@ int launch_k2(Ctx& c, K2Launch& L, int slot, cudaStream_t st) {
     else k2_moment<true, false, true><<<grid, kThreads, kK2SmemBytesDual, st>>>(L.a0, L.a1, L.b, L.p);
     CU_TRY(cudaGetLastError());
     count_launch(c);
+    // executed DMMA flops: two 128 x 64 accumulators per full tile, K padded to whole 16-element stages
+    c.flops[L.mode == 3 ? 2 : 1] += (double)L.total_cost / 16.0 * 2.0 * 2.0 * kTileM * kTileN * (double)kKB *
+                                    L.p.nk_inner * L.p.n_outer;
     if (det && grid > 1) {
         if (L.mode == 3) k2_fixup<true><<<grid, 256, 0, st>>>(L.p, grid);
         else k2_fixup<false><<<grid, 256, 0, st>>>(L.p, grid);
@@ -717,6 +720,11 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
             CU_TRY(cudaEventRecord(c.t1_free[buf], sc));
             count_launch(c);
             c.last_plan[5]++;
+            {   // executed DMMA flops of the launch (padding rows / columns included)
+                double units = 0.0;
+                for (const K1Tile& t : tiles) units += (t.mbv > 0 ? 8.0 * t.mbv : (double)kTileM) * 8.0 * (t.nb1 + t.nb2);
+                c.flops[0] += 2.0 * units * (double)kKB * nk1;
+            }
 
             // ---- K2: accumulate the moments of this chunk ----
             double* const acc_set = c.acc.p + (size_t)4 * set * acc_n;

@@ -99,6 +99,7 @@ struct agf2_b200_ctx {
     size_t events_used = 0;
     int64_t last_plan[6] = {0, 0, 0, 0, 0, 0};   // factorised, PAIR, DIAG, OS, ASYM items, k1_form launches
     double last_ms[4] = {0, 0, 0, 0};            // k1_form, k2_moment (pairs), M build, Coulomb step (GEMM + k2)
+    double flops[3] = {0, 0, 0};                 // executed FP64 tensor flops since the last reset: k1_form, k2_moment, GEMM
     int64_t last_comm_bytes[2] = {0, 0};         // bytes this rank sent over NVLink in the last call: all-gather, all-reduce
 };
 

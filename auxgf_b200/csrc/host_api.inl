@@ -385,6 +385,17 @@ int agf2_b200_ctx_last_comm_bytes(agf2_b200_ctx* ctx, int64_t* bytes2) {
     return 0;
 }
 
+int agf2_b200_ctx_flop_counters(agf2_b200_ctx* ctx, double* flops3, int reset) {
+    int s;
+    Ctx* c = resolve_ctx(ctx, &s);
+    if (!c) return s;
+    for (int k = 0; k < 3; ++k) {
+        if (flops3) flops3[k] = c->flops[k];
+        if (reset) c->flops[k] = 0.0;
+    }
+    return 0;
+}
+
 int agf2_b200_last_kernel_ms(double* k1, double* k2) {
     int s;
     Ctx* c = resolve_ctx(nullptr, &s);
@@ -589,6 +600,25 @@ int agf2_b200_host_unregister(const void* ptr) {
     if (!ptr) return fail(AGF2_B200_EINVAL, "bad argument");
     CU_TRY(cudaHostUnregister(const_cast<void*>(ptr)));
     return 0;
+}
+
+// C (a_rows x b_rows, row-major, or its transpose) = / += A (a_rows x k) . B (b_rows x k)^T on the library's own
+// DMMA / TMA / stream-K pipeline; all pointers device memory, k contiguous in A and B.
+int agf2_b200_ctx_gemm(agf2_b200_ctx* ctx, const double* a, int64_t a_rows, int64_t lda, const double* b, int64_t b_rows,
+                       int64_t ldb, int64_t k, double* c_out, int64_t ldc, int transpose, int accumulate, void* stream)
+{
+    int s;
+    Ctx* c = resolve_ctx(ctx, &s);
+    if (!c) return s;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard guard(c->device);
+    Gemm g;
+    g.a = a; g.a_rows = a_rows; g.lda = lda;
+    g.b = b; g.b_rows = b_rows; g.ldb = ldb;
+    g.k = k; g.c = c_out; g.ldc = ldc;
+    g.transpose = transpose != 0;
+    g.accumulate = accumulate != 0;
+    return run_gemm(*c, g, (cudaStream_t)stream);
 }
 
 // ---- drop-in symbols (reference signatures) ---------------------------------------------------------

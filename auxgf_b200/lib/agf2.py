@@ -41,7 +41,8 @@ SYMBOLS = [
     "agf2_b200_comm_get_unique_id", "agf2_b200_comm_init", "agf2_b200_comm_info", "agf2_b200_comm_allreduce",
     "agf2_b200_comm_allgather", "agf2_b200_comm_broadcast", "agf2_b200_comm_barrier", "agf2_b200_comm_destroy",
     "agf2_b200_ctx_moments_rhf_dev", "agf2_b200_ctx_moments_uhf_dev", "agf2_b200_ctx_build_part_loop_rhf",
-    "agf2_b200_ctx_build_part_loop_uhf", "agf2_b200_host_register", "agf2_b200_host_unregister",
+    "agf2_b200_ctx_build_part_loop_uhf", "agf2_b200_host_register", "agf2_b200_host_unregister", "agf2_b200_ctx_gemm",
+    "agf2_b200_ctx_flop_counters",
 ]
 
 
@@ -111,6 +112,8 @@ _libagf2.agf2_b200_ctx_moments_uhf_dev.argtypes = [_vp, _vp, _i64, _vp, _i64, _v
 _libagf2.agf2_b200_ctx_build_part_loop_rhf.argtypes = [_vp, _in2, _in2, _in1, _in1] + [_i64] * 6 + [_dbl, _dbl, _out2, _out2]
 _libagf2.agf2_b200_ctx_build_part_loop_uhf.argtypes = [_vp, _in2, _in2, _in2, _in1, _in1, _in1, _in1] + [_i64] * 8 + \
     [_dbl, _dbl, _out2, _out2]
+_libagf2.agf2_b200_ctx_gemm.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp]
+_libagf2.agf2_b200_ctx_flop_counters.argtypes = [_vp, ctypes.POINTER(_dbl), ctypes.c_int]
 _libagf2.agf2_b200_host_register.argtypes = [_vp, _i64]
 _libagf2.agf2_b200_host_unregister.argtypes = [_vp]
 # the reference's own void symbols (drop-in ABI; argtypes as auxgf/lib/agf2.py:28-60)
@@ -206,6 +209,13 @@ def sticky_status(clear=False):
     """(status, message) of the first failure of a ``void`` drop-in call (they cannot return one); 0 = none."""
     st = int(_libagf2.agf2_b200_sticky_status(1 if clear else 0))
     return st, (_libagf2.agf2_b200_last_error().decode() if st else "")
+
+
+def flop_counters(reset=False, ctx=None):
+    """FP64 tensor-core flops executed since the last reset: (k1_form, k2_moment, general GEMM), padding included."""
+    out = (_dbl * 3)()
+    check(_libagf2.agf2_b200_ctx_flop_counters(ctx, out, 1 if reset else 0))
+    return tuple(out)
 
 
 def last_comm_bytes(ctx=None):
@@ -463,6 +473,21 @@ def moments_uhf_multi(ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, os_fac
     check(_libagf2.agf2_b200_ctx_build_part_loop_uhf(None, ixq_a, qja_a, qja_b, ei_a, ei_b, ea_a, ea_b, nphys, oa, ob,
                                                      va, vb, naux, 0, oa, os_factor, ss_factor, vv, vev))
     return vv, vev
+
+
+def gemm_dev(a, b, out=None, transpose=False, accumulate=False, ctx=None):
+    """out = a @ b.T (``transpose``: out holds the transpose) on the library's DMMA pipeline.  a: (m, k), b: (n, k)
+    CUDA f64 tensors, last dimension contiguous, even row pitch."""
+    import torch
+    m, k = a.shape
+    n = b.shape[0]
+    assert b.shape[1] == k and a.stride(1) == 1 and b.stride(1) == 1
+    if out is None:
+        out = torch.empty((n, m) if transpose else (m, n), dtype=torch.float64, device=a.device)
+    check(_libagf2.agf2_b200_ctx_gemm(ctx, a.data_ptr(), m, a.stride(0), b.data_ptr(), n, b.stride(0), k,
+                                      out.data_ptr(), out.stride(0), 1 if transpose else 0, 1 if accumulate else 0,
+                                      torch.cuda.current_stream(a.device).cuda_stream))
+    return out
 
 
 def host_register(a):

@@ -113,6 +113,9 @@ int agf2_b200_ctx_set_option(agf2_b200_ctx *ctx, const char *name, int64_t value
 int agf2_b200_ctx_last_stage_ms(agf2_b200_ctx *ctx, double *ms4);
 int agf2_b200_ctx_last_plan(agf2_b200_ctx *ctx, int64_t *info6);
 int agf2_b200_ctx_last_comm_bytes(agf2_b200_ctx *ctx, int64_t *bytes2);
+/* FP64 tensor-core flops the launches of this context EXECUTED since the last reset (tile padding included):
+ * [0] k1_form, [1] k2_moment (pair moments, M build, Coulomb step), [2] general GEMM. */
+int agf2_b200_ctx_flop_counters(agf2_b200_ctx *ctx, double *flops3, int reset);
 
 /* ---- communicator: one rank per context, NCCL over NVLink / NVSwitch -------------------------------
  * Replaces comm.Reduce + comm.Bcast of auxgf/util/mpi.py:60-64 (auxgf/mpi/agf2/optragf2.py:394-395).
@@ -162,6 +165,14 @@ int agf2_b200_ctx_build_part_loop_uhf(agf2_b200_ctx *ctx, const double *ixq_a, c
                                       int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
                                       int64_t istart, int64_t iend, double os_factor, double ss_factor,
                                       double *vv, double *vev);
+
+/* General FP64 GEMM on the library's own DMMA / TMA / stream-K pipeline (the kernel behind the Coulomb
+ * factorisation's T = ixq [M0|M1], the DF transform and the exchange matrix):
+ *     C (a_rows x b_rows, row-major, pitch ldc; transpose != 0: C^T is stored)  =  A (a_rows x k) B (b_rows x k)^T
+ * (+= when accumulate != 0).  Device pointers, 16-byte aligned, k contiguous, lda/ldb even.  Bit-reproducible. */
+int agf2_b200_ctx_gemm(agf2_b200_ctx *ctx, const double *a, int64_t a_rows, int64_t lda, const double *b,
+                       int64_t b_rows, int64_t ldb, int64_t k, double *c, int64_t ldc, int transpose,
+                       int accumulate, void *stream);
 
 /* Optional: page-lock a caller-owned host buffer (cudaHostRegister) so that the uploads of the
  * host-pointer calls are asynchronous DMA transfers; pageable memory works too. */

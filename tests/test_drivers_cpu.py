@@ -62,6 +62,18 @@ def test_aux_dot_eq_and_io(tmp_path):
     a.save(str(tmp_path / "se.pickle"))
     b = Aux.load(str(tmp_path / "se.pickle"))
     assert b == a and b.chempot == a.chempot
+    # checkpoint format of the reference (auxgf/aux/aux.py:735-761: pickle of __dict__ = _ener, _coup, chempot):
+    # what we write is what the reference's Aux.load setattr()s, and a reference-written file loads here
+    import pickle
+    with open(str(tmp_path / "se.pickle"), "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"_ener", "_coup", "chempot"} and d["_coup"].shape == (4, 6)
+    with open(str(tmp_path / "ref.pickle"), "wb") as f:
+        pickle.dump({"_ener": e, "_coup": v, "chempot": -0.2}, f)
+    assert Aux.load(str(tmp_path / "ref.pickle")) == a
+    with open(str(tmp_path / "old.pickle"), "wb") as f:              # round-1 files
+        pickle.dump({"e": e, "v": v, "chempot": -0.2}, f)
+    assert Aux.load(str(tmp_path / "old.pickle")) == a
 
 
 def test_checkpoint_option(oracle_backend, tmp_path, monkeypatch):

@@ -89,8 +89,18 @@ def test_optragf2_cuda_vs_oracle():
     assert abs(g.e_1body - r.e_1body) < 1e-8 and abs(g.e_2body - r.e_2body) < 1e-8
     assert abs(g.ip[0] - r.ip[0]) < 1e-8 and abs(g.ea[0] - r.ea[0]) < 1e-8
     assert abs(g.chempot - r.chempot) < 1e-7
+    # moments: 1e-10 wherever both drivers start from the same state -- the construction-time (MP2) build, and one
+    # build() from the oracle driver's final state; after independent Fock loops (dtol = 1e-8) only to 1e-8
+    g0 = _run("OptRAGF2", hf, 0)[0]
+    r0 = _with_oracle(lambda: _run("OptRAGF2", hf, 0)[0])
     for k in (0, 1):
+        assert relerr(g0.se.moment(k), r0.se.moment(k)) < 1e-10
         assert relerr(g.se.moment(k), r.se.moment(k)) < 1e-8
+    g.se, g.gf, g.rdm1 = r.se.copy(), r.gf.copy(), r.rdm1.copy()
+    g.build()
+    _with_oracle(r.build)
+    for k in (0, 1):
+        assert relerr(g.se.moment(k), r.se.moment(k)) < 1e-10
 
 
 def test_build_part_moments_cuda_vs_oracle():
@@ -116,6 +126,15 @@ def test_optuagf2_cuda_vs_oracle():
     r, r0 = _with_oracle(lambda: _run("OptUAGF2", uhf, 2))
     assert abs(e0 - r0) < 1e-8 and abs(g.e_tot - r.e_tot) < 1e-8
     assert abs(g.ip[0] - r.ip[0]) < 1e-8 and abs(g.ea[0] - r.ea[0]) < 1e-8
+    g0 = _run("OptUAGF2", uhf, 0)[0]
+    r0 = _with_oracle(lambda: _run("OptUAGF2", uhf, 0)[0])
     for s in range(2):
         for k in (0, 1):
-            assert relerr(g.se[s].moment(k), r.se[s].moment(k)) < 1e-8
+            assert relerr(g0.se[s].moment(k), r0.se[s].moment(k)) < 1e-10      # same inputs: north_star tolerance
+            assert relerr(g.se[s].moment(k), r.se[s].moment(k)) < 1e-8         # after independent Fock loops
+    g.se = tuple(x.copy() for x in r.se); g.gf = tuple(x.copy() for x in r.gf); g.rdm1 = r.rdm1.copy()
+    g.build()
+    _with_oracle(r.build)
+    for s in range(2):
+        for k in (0, 1):
+            assert relerr(g.se[s].moment(k), r.se[s].moment(k)) < 1e-10

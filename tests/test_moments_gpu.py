@@ -273,3 +273,88 @@ def test_edge_cases_and_errors(lib):
         lib.moments_rhf_dev(*d, part=3, nparts=2)
     with pytest.raises(lib.Agf2B200Error):
         lib.moments_rhf_dev(T(ixq, (o, p, n)), T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))   # odd pitch (v = 9)
+
+
+def test_bit_repeatability(lib):
+    """Deterministic mode (default): stream-K partial tiles are summed in CTA order by k2_fixup and every stream has
+    its own accumulator set, so the same build gives the same bits -- many chunks on two streams, Coulomb
+    factorisation, slices, UHF, host-pointer and device-resident entry points."""
+    import torch
+    lib.set_workspace_bytes(2 << 20)          # many chunks: both streams busy
+    try:
+        o, v, n, p = 20, 60, 200, 300
+        ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 70)
+        runs = [lib.moments_rhf(ixq, qja, ei, ea, p) for _ in range(3)]
+        for r in runs[1:]:
+            assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[1], runs[0][1])
+        a = [lib.moments_rhf(ixq, qja, ei, ea, p, 3, 11, 1.2, 1.0 / 3.0) for _ in range(2)]
+        assert np.array_equal(a[0][0], a[1][0]) and np.array_equal(a[0][1], a[1][1])
+        args = orc.synth_uhf(12, 40, 11, 41, 150, 200, 71)
+        u = [lib.moments_uhf(*args, 200) for _ in range(2)]
+        assert np.array_equal(u[0][0], u[1][0]) and np.array_equal(u[0][1], u[1][1])
+        dev = torch.device("cuda", 0)
+        T = lambda x, sh: torch.from_numpy(np.ascontiguousarray(x)).reshape(sh).to(dev)  # noqa: E731
+        d = (T(ixq, (o, p, n)), T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))
+        g = [torch.stack(lib.moments_rhf_dev(*d)).cpu().numpy() for _ in range(2)]
+        assert np.array_equal(g[0], g[1])
+        assert np.array_equal(g[0][0], runs[0][0])          # host-pointer and device-resident paths agree bit for bit
+        # the non-deterministic mode (red.global.add) agrees to rounding
+        lib.set_deterministic(False)
+        nd = lib.moments_rhf(ixq, qja, ei, ea, p)
+        assert relerr(nd[0], runs[0][0]) < 1e-13 and relerr(nd[1], runs[0][1]) < 1e-13
+    finally:
+        lib.set_deterministic(True)
+        lib.set_workspace_bytes(40 << 20)
+
+
+@pytest.mark.parametrize("shape", [(300, 200, 96), (256, 64, 16), (1, 1, 1), (130, 70, 37), (513, 129, 260),
+                                   (2000, 1000, 555), (64, 3000, 48)])
+def test_general_gemm(lib, shape):
+    """agf2_b200_ctx_gemm (k2_moment general-GEMM instantiation, 256 x 64 tiles, stream-K + fixed-order fixup)
+    against torch.matmul in FP64: plain, transposed output, accumulate, padded pitches; bit-reproducible."""
+    import torch
+    m, n, k = shape
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev); g.manual_seed(m * 7 + n)
+    kp = k + (k & 1) + 2                      # padded (even) pitch
+    a = torch.randn((m, kp), generator=g, device=dev, dtype=torch.float64)[:, :k]
+    b = torch.randn((n, kp), generator=g, device=dev, dtype=torch.float64)[:, :k]
+    ref = a @ b.T
+    scale = float(ref.abs().max()) + 1e-300
+    c = lib.gemm_dev(a, b)
+    assert float((c - ref).abs().max()) / scale < 1e-13
+    assert torch.equal(c, lib.gemm_dev(a, b))
+    ct = lib.gemm_dev(a, b, transpose=True)
+    assert torch.equal(ct, c.T.contiguous())
+    acc = torch.full((m, n + 3), 2.0, device=dev, dtype=torch.float64)[:, :n]     # pitch n + 3, += semantics
+    lib.gemm_dev(a, b, out=acc, accumulate=True)
+    assert float((acc - 2.0 - ref).abs().max()) / scale < 1e-13
+
+
+def test_contexts(lib):
+    """User-created contexts: own options (the process defaults are untouched), own scratch; destroying one
+    leaves the default context working; the void drop-ins surface failures through the sticky status."""
+    import ctypes
+    h = ctypes.c_void_p()
+    lib.check(lib._libagf2.agf2_b200_ctx_create(-1, ctypes.byref(h)))
+    lib.set_option("workspace_bytes", 1 << 20, ctx=h)
+    lib.set_option("deterministic", 0, ctx=h)
+    dev = ctypes.c_int(-1)
+    lib.check(lib._libagf2.agf2_b200_ctx_get_device(h, ctypes.byref(dev)))
+    assert dev.value == 0
+    o, v, n, p = 9, 30, 64, 50
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 80)
+    vv = np.zeros((p, p)); vev = np.zeros((p, p))
+    lib.check(lib._libagf2.agf2_b200_ctx_build_part_loop_rhf(h, ixq, qja, ei, ea, p, o, v, n, 0, o, 1.0, 1.0, vv, vev))
+    rv, rev = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o)
+    assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL
+    lib.check(lib._libagf2.agf2_b200_ctx_destroy(h))
+    _check_rhf(lib, o, v, n, p, seed=80)                    # default context still alive
+    assert lib.comm_info() == (0, 1)
+    # sticky status of the void drop-ins: a bad call leaves vv/vev untouched and records the failure
+    assert lib.sticky_status(clear=True)[0] == 0
+    vv = np.full((p, p), 7.0); vev = np.full((p, p), 7.0)
+    lib._libagf2.build_part_loop_rhf(ixq, qja, ei, ea, 0, o, v, n, 0, o, vv, vev)        # nphys = 0
+    st, msg = lib.sticky_status(clear=True)
+    assert st != 0 and "build_part_loop_rhf" in msg and (vv == 7.0).all() and (vev == 7.0).all()
+    assert lib.sticky_status()[0] == 0
