@@ -295,22 +295,32 @@ int run_gemm(Ctx& c, const Gemm& g, cudaStream_t st) {
 
     const int64_t third = std::max<int64_t>(g.nbatch, g.n_outer);
     K2Launch L;
-    auto map3 = [&](CUtensorMap* m, const double* base, int64_t rows, int64_t ld, int64_t third_stride) -> int {
+    // 3-D operand map (k, rows, third); when the third (batch / outer-K) stride is the smaller one the two outer
+    // dimensions are listed in ascending stride order, (k, third, rows), and the kernel swaps the coordinates
+    auto map3 = [&](CUtensorMap* m, const double* base, int64_t rows, int64_t ld, int64_t third_stride, bool swap) -> int {
         const bool has3 = third > 1 && third_stride > 0;
+        if (swap) {
+            cuuint64_t d[3] = {(cuuint64_t)g.k, (cuuint64_t)third, (cuuint64_t)rows};
+            cuuint64_t s[2] = {(cuuint64_t)third_stride * 8, (cuuint64_t)ld * 8};
+            cuuint32_t b[3] = {kKB, 1, 64};
+            return make_map(c, m, base, 3, d, s, b);
+        }
         cuuint64_t d[3] = {(cuuint64_t)g.k, (cuuint64_t)rows, (cuuint64_t)(has3 ? third : 1)};
         cuuint64_t s[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(has3 ? third_stride : rows * ld) * 8};
         cuuint32_t b[3] = {kKB, 64, 1};
         return make_map(c, m, base, 3, d, s, b);
     };
-    if (int r = map3(&L.a0, g.a, g.a_rows, g.lda, g.a_third)) return r;
+    const bool swap_a = third > 1 && g.a_third > 0 && g.a_third < g.lda;
+    const bool swap_b = third > 1 && g.b_third > 0 && g.b_third < g.ldb;
+    if (int r = map3(&L.a0, g.a, g.a_rows, g.lda, g.a_third, swap_a)) return r;
     if (plain) {
         // second accumulator = rows +128 of the same operand (256 x 64 output tiles)
-        if (g.a_rows > kTileM) { if (int r = map3(&L.a1, g.a + kTileM * g.lda, g.a_rows - kTileM, g.lda, g.a_third)) return r; }
+        if (g.a_rows > kTileM) { if (int r = map3(&L.a1, g.a + kTileM * g.lda, g.a_rows - kTileM, g.lda, g.a_third, swap_a)) return r; }
         else L.a1 = L.a0;
     } else {
-        if (int r = map3(&L.a1, g.a1, g.a_rows, g.lda, g.a_third)) return r;
+        if (int r = map3(&L.a1, g.a1, g.a_rows, g.lda, g.a_third, swap_a)) return r;
     }
-    if (int r = map3(&L.b, g.b, g.b_rows, g.ldb, g.b_third)) return r;
+    if (int r = map3(&L.b, g.b, g.b_rows, g.ldb, g.b_third, swap_b)) return r;
     L.mode = 3;
     L.total_cost = 16 * ntiles;
     K2Params p = k2_params();
@@ -324,6 +334,7 @@ int run_gemm(Ctx& c, const Gemm& g, cudaStream_t st) {
     p.rows_valid = (int)g.a_rows; p.cols_valid = (int)g.b_rows;
     p.vev_rows_valid = plain ? (int)std::max<int64_t>(0, g.a_rows - kTileM) : (g.c1 ? (int)g.a_rows : 0);
     p.sym = 0; p.mask = 0;
+    p.swap_a = swap_a ? 1 : 0; p.swap_b = swap_b ? 1 : 0;
     p.a_row_step = (int)row_step;
     p.transpose_out = g.transpose ? 1 : 0;
     p.store = g.accumulate ? 0 : 1;

@@ -580,8 +580,13 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                     tma_load_3d(st + 8192, &mapA0, k0, ra + 64, oa, fb);
                 }
                 if (kDual) {
-                    tma_load_3d(st + kOffA1, &mapA1, k0, ra, oa, fb);
-                    tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, ra + 64, oa, fb);
+                    if (p.swap_a) {
+                        tma_load_3d(st + kOffA1, &mapA1, k0, oa, ra, fb);
+                        tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, oa, ra + 64, fb);
+                    } else {
+                        tma_load_3d(st + kOffA1, &mapA1, k0, ra, oa, fb);
+                        tma_load_3d(st + kOffA1 + 8192, &mapA1, k0, ra + 64, oa, fb);
+                    }
                 }
                 if (p.swap_b) tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, ob, rb, fb);
                 else tma_load_3d(st + kOffB, &mapB, k0 + p.b_k_off, rb, ob, fb);
