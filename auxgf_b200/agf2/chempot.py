@@ -11,7 +11,9 @@ from auxgf_b200.util import find_chempot
 
 
 def diag_fock_ext(se, fock, nelec, chempot=0.0, occupancy=2.0, buf=None):
-    w, v = se.eig(fock, chempot=chempot, out=buf)
+    """-> (w, v_phys, chempot, error): eigenvalues and the PHYSICAL rows of the eigenvectors of the extended Fock
+    matrix (the auxiliary rows never leave the GPU), Aufbau chemical potential and electron-number error."""
+    w, v = se.eig_phys(fock, chempot=chempot, out=buf)
     chempot_phys, error = find_chempot(se.nphys, nelec, (w, v), occupancy=occupancy)
     return w, v, chempot_phys, error
 
@@ -43,7 +45,9 @@ def gradient(x, se, fock, nelec, occupancy=2.0, buf=None, return_val=False, memo
     w, v, chempot, error = solve(x, se, fock, nelec, occupancy, buf)
     nocc = int(np.sum(w < chempot))
     n = se.nphys
-    h_1 = -(v[n:, nocc:].T @ v[n:, :nocc])
+    # chempot.py:96-99 uses the auxiliary rows:  h_1 = -v_aux[:, vir]^T v_aux[:, occ].  The eigenvectors are
+    # orthonormal, so for an occupied / virtual pair  v_aux^T v_aux = -v_phys^T v_phys : the physical rows suffice
+    h_1 = v[:n, nocc:].T @ v[:n, :nocc]
     z_ai = -h_1 / (w[None, :nocc] - w[nocc:, None])
     c_occ = v[:n, nocc:] @ z_ai
     rdm1 = (v[:n, :nocc] @ c_occ.T) * 4
@@ -62,5 +66,5 @@ def minimize(se, fock, nelec, occupancy=2.0, buf=None, x0=0.0, tol=1e-6, maxiter
         kwargs["jac"] = lambda x, *a: np.array([gradient(x, *a[:5], memo=a[5])])
     opt = optimize.minimize(objective, args=args, **kwargs)
     se._ener -= float(np.ravel(opt.x)[0])
-    se.chempot = find_chempot(se.nphys, nelec, se.eig(fock), occupancy=occupancy)[0]
+    se.chempot = find_chempot(se.nphys, nelec, se.eig_phys(fock), occupancy=occupancy)[0]
     return se, opt

@@ -137,8 +137,8 @@ class OptRAGF2:
 
     def solve_dyson(self):
         """gf = eigenpairs of the extended Fock matrix projected on the physical space (method.py:134-147)."""
-        e, c = self.se.eig(self.get_fock())
-        self.gf = self.se.new(e, c[:self.se.nphys])
+        e, c = self.se.eig_phys(self.get_fock())
+        self.gf = self.se.new(e, c)
 
     # ---------------------------------------------------------------------------------------------
     @record_time("fock")

@@ -61,8 +61,8 @@ class OptUAGF2(OptRAGF2):
         fock = self.get_fock()
         gf = []
         for s in range(2):
-            e, c = self.se[s].eig(fock[s])
-            gf.append(self.se[s].new(e, c[:self.se[s].nphys]))
+            e, c = self.se[s].eig_phys(fock[s])
+            gf.append(self.se[s].new(e, c))
         self.gf = tuple(gf)
 
     @record_time("fock")

@@ -94,6 +94,25 @@ class Aux:
         h_ext = self.as_hamiltonian(h_phys, chempot=chempot, out=out)
         return backend.get().eigh(h_ext)
 
+    def eig_phys(self, h_phys, chempot=0.0, out=None):
+        """(w, v[:nphys]) of the extended Hamiltonian: eigenvalues and the physical rows of the eigenvectors -- all
+        that the Dyson equation, the density matrix and the chemical-potential gradient need (method.py:134-147,
+        fock.py:119-143, chempot.py:77-118).  The couplings are uploaded once per ``Aux`` (they stay in HBM while the
+        Fock loop re-diagonalises with new ``h_phys`` / ``chempot``); the matrix is assembled on the device and only
+        w and the nphys rows come back."""
+        solver = self._fock_solver()
+        return solver.solve(np.asarray(h_phys, dtype=np.float64), self._ener, shift=chempot)
+
+    def _fock_solver(self):
+        solver = getattr(self, "_solver", None)
+        if solver is None:
+            solver = self._solver = backend.get().fock_solver()
+            self._solver_for = None
+        if self._solver_for is not self._coup:      # couplings replaced (sort, new poles): upload again
+            solver.set_couplings(self._coup)
+            self._solver_for = self._coup
+        return solver
+
     def dot(self, h_phys, vec, chempot=0.0):
         """``as_hamiltonian(h_phys, chempot) @ vec`` without building the extended matrix (aux.py:420-465)."""
         h_phys = np.asarray(h_phys)

@@ -3,6 +3,8 @@ special case.  ``energy_2body_aux`` is restated as one matrix product (the refer
 occupied Green's-function poles with a five-operand einsum, energy.py:43-49)."""
 import numpy as np
 
+from auxgf_b200 import backend
+
 
 def energy_2body_aux(gf, se, both_sides=False):
     if isinstance(se, (tuple, list)):
@@ -11,10 +13,11 @@ def energy_2body_aux(gf, se, both_sides=False):
         return sum(energy_2body_aux(gfs[i], se[i], both_sides=both_sides) for i in range(n)) / n
     nphys = se.nphys
 
+    be = backend.get()
+
     def half(gv, ge, sv, sen, sign):
-        # sum_{l,k} (sum_x gv[x,l] sv[x,k])^2 * sign / (ge[l] - sen[k])
-        ovl = gv[:nphys].T @ sv
-        return float(np.sum(ovl * ovl * (sign / (ge[:, None] - sen[None, :]))))
+        # sum_{l,k} (sum_x gv[x,l] sv[x,k])^2 * sign / (ge[l] - sen[k]): one GEMM + reduction, on the device
+        return sign * be.energy_2body(gv[:nphys], ge, sv, sen)
 
     go, so = gf.e < gf.chempot, se.e < se.chempot
     e2b = half(gf.v[:, go], gf.e[go], se.v[:, ~so], se.e[~so], 1.0)

@@ -39,6 +39,13 @@ class CudaBackend:
     def eigh(self, a):
         return self.lib.eigh(np.ascontiguousarray(a, dtype=np.float64))
 
+    def fock_solver(self):
+        """Extended-Fock eigensolver with the couplings resident in HBM (``lib.FockSolver``)."""
+        return self.lib.FockSolver()
+
+    def energy_2body(self, gv, ge, sv, se):
+        return self.lib.energy_2body(gv, ge, sv, se)
+
     # device-resident DF tensor + fused ao2mo/moment build (see auxgf_b200.lib.agf2.DeviceERI)
     def stage_eri(self, eri, nphys, sym_in="s2"):
         return self.lib.DeviceERI(eri, nphys, packed=(sym_in == "s2"))

@@ -669,7 +669,9 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
     }
 
     c.events_used = 0;
-    int64_t& chunk_idx = c.chunk_counter;   // global: tile staging buffers alternate across calls too
+    // chunk c of THIS call uses stream / ring buffer / accumulator set (c & 1): the assignment (and with it the
+    // summation order) does not depend on what ran before
+    int64_t chunk_idx = 0;
     std::vector<K1Tile> tiles;
 
     auto run_chunks = [&](const std::vector<Item>& items, bool sym) -> int {

@@ -499,6 +499,77 @@ def host_unregister(a):
     check(_libagf2.agf2_b200_host_unregister(a.ctypes.data))
 
 
+_libagf2.agf2_b200_fock_create.argtypes = [ctypes.POINTER(_vp)]
+_libagf2.agf2_b200_fock_destroy.argtypes = [_vp]
+_libagf2.agf2_b200_fock_set_couplings.argtypes = [_vp, _vp, _i64, _i64]
+_libagf2.agf2_b200_fock_solve.argtypes = [_vp, _vp, _vp, _dbl, _vp, _vp]
+_libagf2.agf2_b200_fock_solve_async.argtypes = [_vp, _vp, _vp, _dbl, _vp, _vp]
+_libagf2.agf2_b200_fock_wait.argtypes = [_vp]
+_libagf2.agf2_b200_energy_2body.argtypes = [_vp, _vp, _i64, _vp, _vp, _i64, _i64, ctypes.POINTER(_dbl)]
+SYMBOLS += ["agf2_b200_fock_create", "agf2_b200_fock_destroy", "agf2_b200_fock_set_couplings", "agf2_b200_fock_solve",
+            "agf2_b200_fock_solve_async", "agf2_b200_fock_wait", "agf2_b200_energy_2body"]
+
+
+class FockSolver:
+    """Eigensolver of the extended Fock matrix [[F, v], [v^T, diag(e - shift)]] with the couplings ``v`` resident in
+    HBM (``agf2_b200_fock_*``): the matrix is assembled on the device, cuSOLVER dsyevd runs in a reused workspace and
+    only ``w`` and the physical rows of the eigenvectors come back.  Replaces np.linalg.eigh of auxgf/aux/eig.py:23-33
+    inside the Fock loop (auxgf/agf2/fock.py:119-143, chempot.py:11-49)."""
+
+    def __init__(self):
+        h = _vp()
+        check(_libagf2.agf2_b200_fock_create(ctypes.byref(h)))
+        self._h = h
+        self._v = None
+        self._out = None
+
+    def set_couplings(self, v):
+        v = _c(v, 2)
+        self._v = v                     # keeps the identity the cache in Aux.eig_phys compares
+        self.nphys, self.naux = v.shape
+        check(_libagf2.agf2_b200_fock_set_couplings(self._h, v.ctypes.data, self.nphys, self.naux))
+
+    def solve_async(self, fock, e, shift=0.0):
+        fock = _c(fock, 2); e = _c(e, 1)
+        assert fock.shape == (self.nphys, self.nphys) and e.size == self.naux
+        n = self.nphys + self.naux
+        w = np.empty(n); v = np.empty((self.nphys, n))
+        check(_libagf2.agf2_b200_fock_solve_async(self._h, fock.ctypes.data, e.ctypes.data, float(shift), w.ctypes.data,
+                                                  v.ctypes.data))
+        self._out = (w, v)
+
+    def wait(self):
+        check(_libagf2.agf2_b200_fock_wait(self._h))
+        out, self._out = self._out, None
+        return out
+
+    def solve(self, fock, e, shift=0.0):
+        self.solve_async(fock, e, shift)
+        return self.wait()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _libagf2.agf2_b200_fock_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def energy_2body(gv, ge, sv, se):
+    """sum_{l,k} (sum_x gv[x,l] sv[x,k])^2 / (ge[l] - se[k]) on the device; gv (nphys, nl), sv (nphys, nk) as in
+    the reference's Aux couplings (auxgf/aux/energy.py:43-49)."""
+    gvt = _c(np.asarray(gv).T, 2); svt = _c(np.asarray(sv).T, 2)
+    ge = _c(ge, 1); se = _c(se, 1)
+    out = _dbl(0.0)
+    check(_libagf2.agf2_b200_energy_2body(gvt.ctypes.data, ge.ctypes.data, ge.size, svt.ctypes.data, se.ctypes.data,
+                                          se.size, gvt.shape[1] if ge.size else svt.shape[1], ctypes.byref(out)))
+    return out.value
+
+
 def compress_dev(vv, vev):
     import torch
     n = vv.shape[0]

@@ -250,6 +250,30 @@ int agf2_b200_compress(const double *vv, const double *vev, int64_t nphys, doubl
  * w: (n) ascending; v: (n, n) row-major with eigenvectors in COLUMNS (NumPy convention). */
 int agf2_b200_eigh(const double *a, int64_t n, double *w, double *v, int on_device);
 
+/* Extended-Fock eigensolver with resident couplings -- the inner loop of auxgf/agf2/fock.py:119-143 and
+ * auxgf/agf2/chempot.py:11-49 diagonalises  [[F, v], [v^T, diag(e - shift)]]  hundreds of times per AGF2 iteration
+ * with the same couplings v.  set_couplings uploads v (host, (nphys, naux) row-major) once; every solve sends only
+ * F (nphys^2) and e (naux), assembles the matrix on the device, runs cuSOLVER dsyevd in a reused workspace and returns
+ * the eigenvalues w (nphys + naux, ascending) and the PHYSICAL rows of the eigenvectors v_phys ((nphys, nphys + naux)
+ * row-major) -- all the Fock loop, the density matrix and the chemical-potential gradient use.  solve_async / wait:
+ * solves on different handles (alpha / beta) overlap on the device. */
+typedef struct agf2_b200_fock agf2_b200_fock;
+int agf2_b200_fock_create(agf2_b200_fock **out);
+int agf2_b200_fock_destroy(agf2_b200_fock *h);
+int agf2_b200_fock_set_couplings(agf2_b200_fock *h, const double *v, int64_t nphys, int64_t naux);
+int agf2_b200_fock_solve(agf2_b200_fock *h, const double *fock, const double *e, double shift, double *w,
+                         double *v_phys);
+int agf2_b200_fock_solve_async(agf2_b200_fock *h, const double *fock, const double *e, double shift, double *w,
+                               double *v_phys);
+int agf2_b200_fock_wait(agf2_b200_fock *h);
+
+/* Galitskii-Migdal two-body energy term on the device (auxgf/aux/energy.py:43-62 restated as one GEMM + reduction):
+ *     out = sum_{l < nl, k < nk} (sum_x gv[l, x] sv[k, x])^2 / (ge[l] - se[k])
+ * gv (nl, nphys) and sv (nk, nphys): host arrays, pole-major (the transposes of the reference's (nphys, naux)
+ * couplings), ge (nl), se (nk).  The overlap matrix runs on the library's DMMA pipeline. */
+int agf2_b200_energy_2body(const double *gv, const double *ge, int64_t nl, const double *sv, const double *se,
+                           int64_t nk, int64_t nphys, double *out);
+
 /* Device-resident DF tensor ("staged once to HBM") and the per-sector DF transform on the device.
  *   agf2_b200_eri_create : eri is the Cholesky/DF tensor L, either tril-packed (naux, nphys(nphys+1)/2)
  *       as OptRAGF2 keeps it (auxgf/agf2/optragf2.py:159-160, packed != 0) or full (naux, nphys, nphys);

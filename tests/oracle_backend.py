@@ -63,8 +63,35 @@ class _Packed:
         self.a = a
 
 
+class _HostFockSolver:
+    """Host stand-in for lib.FockSolver: dense np.linalg.eigh of the extended matrix (auxgf/aux/eig.py:23-33)."""
+
+    def set_couplings(self, v):
+        self._v = np.asarray(v)
+
+    def solve(self, fock, e, shift=0.0):
+        n, m = self._v.shape
+        h = np.zeros((n + m, n + m))
+        h[:n, :n] = fock
+        h[:n, n:] = self._v
+        h[n:, :n] = self._v.T
+        h[n:, n:][np.diag_indices(m)] = np.asarray(e) - shift
+        w, v = np.linalg.eigh(h)
+        return w, v[:n]
+
+
 class OracleBackend:
     name = "oracle"
+
+    def fock_solver(self):
+        return _HostFockSolver()
+
+    def energy_2body(self, gv, ge, sv, se):
+        """The reference's loop over occupied poles (auxgf/aux/energy.py:43-49)."""
+        out = 0.0
+        for l in range(gv.shape[1]):
+            out += np.einsum("xk,yk,x,y,k->", sv, sv, gv[:, l], gv[:, l], 1.0 / (ge[l] - se))
+        return float(out)
 
     def build_part_loop_rhf(self, ixq, qja, gf_occ, gf_vir, istart, iend, vv=None, vev=None, os_factor=1.0, ss_factor=1.0):
         o, v, p = gf_occ.naux, gf_vir.naux, gf_occ.nphys

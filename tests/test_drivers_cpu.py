@@ -149,7 +149,7 @@ def test_scs_options_are_honoured(oracle_backend):
     assert abs(a.e_mp2 - b.e_mp2) > 1e-6
 
 
-def test_energy_functions_match_reference_loops():
+def test_energy_functions_match_reference_loops(oracle_backend):
     """energy_2body_aux restated as a matrix product == the reference's per-pole loop (energy.py:43-49)."""
     rng = np.random.default_rng(3)
     n = 5
