@@ -668,6 +668,8 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         CU_TRY(cudaStreamWaitEvent(c.stream2, c.ev_start, 0));
     }
 
+    const CUtensorMap* mapA2 = nullptr;     // visiting pole block (pole-sharded builds only)
+    const double* ixq2 = nullptr;
     c.events_used = 0;
     // chunk c of THIS call uses stream / ring buffer / accumulator set (c & 1): the assignment (and with it the
     // summation order) does not depend on what ran before
@@ -719,11 +721,11 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
             record(c, sc, 0, true);
             if (!opt.simple) {
                 k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, sc>>>(
-                    mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev, Wa, Wb,
-                    Ebuf, ldw, nk1);
+                    mapA, mapA2 ? *mapA2 : mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
+                    Wa, Wb, Ebuf, ldw, nk1);
             } else {
                 k1_form_simple<<<(unsigned)tiles.size(), 256, 0, sc>>>(
-                    ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,
+                    ixq, ixq2 ? ixq2 : ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,
                     other ? other->qja : same.qja, other ? other->ld : same.ld, other ? (int)other->nocc : (int)o,
                     other ? (int)other->nvir : (int)v, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
                     Wa, Wb, Ebuf, ldw);

@@ -177,11 +177,12 @@ extern "C" int agf2_b200_ao2mo_sector(agf2_b200_eri* h, const double* v_occ, int
     const int64_t ldn = rup2(N), ldv = rup2(nvir);
     if (int r = grow(h->ixq, (size_t)nocc * P * ldn, false)) return r;
     if (int r = grow(h->qja, (size_t)N * nocc * ldv, false)) return r;
-    if (int r = grow(h->coef, (size_t)2 * P * (nocc + nvir) + (size_t)ldp * (nocc + nvir), false)) return r;
+    if (int r = grow(h->coef, (size_t)(rup2(P * nocc) + rup2(P * nvir)) + (size_t)ldp * (nocc + nvir), false)) return r;
     // coefficients: staged row-major (P, n), then transposed to (n, ldp) so that the contraction index is contiguous
+    // (every piece starts on a 16-byte boundary: TMA operand bases)
     double* co_raw = h->coef.p;
-    double* cv_raw = co_raw + P * nocc;
-    double* coT = cv_raw + P * nvir;
+    double* cv_raw = co_raw + rup2(P * nocc);
+    double* coT = cv_raw + rup2(P * nvir);
     double* cvT = coT + nocc * ldp;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CU_TRY(cudaMemcpyAsync(co_raw, v_occ, (size_t)P * nocc * 8, kind, st));

@@ -49,7 +49,8 @@ struct K1Tile {
     double p11, p12, p21, p22;
     double e1, e2;         // e_i + e_j of out1 / out2
     int mbv;               // > 0: thin tile -- only the first mbv 8-row blocks of the x-block exist (see k1_mainloop_thin)
-    int pad_;
+    int asel1, asel2;      // which (ix|Q) tensor i1 / i2 index: 0 the resident one, 1 the visiting pole block (pole-sharded
+    int pad_;              // builds: ixq is split over the GPUs and blocks of poles travel over NVLink)
 };
 
 constexpr int kK1StageBytes = 2 * kTileM * kKB * 8 + 2 * kTileN * kKB * 8;  // 49152
@@ -281,8 +282,9 @@ __device__ __forceinline__ void k1_thin_tile(const K1Tile& t, const uint8_t* __r
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB0,
-        const __grid_constant__ CUtensorMap mapB1, const K1Tile* __restrict__ tiles,
+k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+        const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+        const K1Tile* __restrict__ tiles,
         const double* __restrict__ ea0, const double* __restrict__ ea1,
         double* __restrict__ W0, double* __restrict__ W1, double* __restrict__ E0,
         long long ldw, int nk)
@@ -311,7 +313,9 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
     if (warp >= kConsumerWarps) {
         reg_dealloc_producer();
         if (warp == kConsumerWarps && lane == 0) {
-            tma_prefetch_desc(&mapA);
+            const CUtensorMap* mA1 = t.asel1 ? &mapA2 : &mapA;
+            const CUtensorMap* mA2 = t.asel2 ? &mapA2 : &mapA;
+            tma_prefetch_desc(mA1);
             tma_prefetch_desc(t.bsel1 ? &mapB1 : &mapB0);
             const int ng1 = (t.nb1 + 1) >> 1, ng2 = (t.nb2 + 1) >> 1;   // 16-column TMA boxes
             const uint32_t stage_tx = (uint32_t)((t.nb1 ? kTileM * kKB * 8 : 0) + (t.nb2 ? kTileM * kKB * 8 : 0) +
@@ -327,8 +331,8 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
                 const uint32_t fb = bar_full + 8 * s;
                 mbar_expect_tx(fb, stage_tx);
                 const int q0 = j * kKB;
-                if (nb1) tma_load_3d(st, &mapA, q0, x0, i1, fb);
-                if (nb2) tma_load_3d(st + 16384, &mapA, q0, x0, i2, fb);
+                if (nb1) tma_load_3d(st, mA1, q0, x0, i1, fb);
+                if (nb2) tma_load_3d(st + 16384, mA2, q0, x0, i2, fb);
                 for (int g = 0; g < ng1; ++g) tma_load_3d(st + 32768 + g * 2048, mB1, a1 + 16 * g, j1, q0, fb);
                 for (int g = 0; g < ng2; ++g) tma_load_3d(st + 40960 + g * 2048, mB2, a2 + 16 * g, j2, q0, fb);
             }
@@ -888,7 +892,7 @@ __global__ void gen_gemm_tiles(K2Tile* __restrict__ tiles, int* __restrict__ cos
 }
 
 // ---- naive debug kernels (same tile lists, no tensor cores, no TMA) ------------------------------
-__global__ void k1_form_simple(const double* __restrict__ ixq, long long ld_ixq, int nphys, int naux,
+__global__ void k1_form_simple(const double* __restrict__ ixq, const double* __restrict__ ixq2, long long ld_ixq, int nphys, int naux,
                                const double* __restrict__ qja0, long long ld_q0, int nocc0, int nvir0,
                                const double* __restrict__ qja1, long long ld_q1, int nocc1, int nvir1,
                                const K1Tile* __restrict__ tiles, const double* __restrict__ ea0,
@@ -907,7 +911,7 @@ __global__ void k1_form_simple(const double* __restrict__ ixq, long long ld_ixq,
                 const int no = t.bsel1 ? nocc1 : nocc0, nv = t.bsel1 ? nvir1 : nvir0;
                 if (t.a1 + c < nv)
                     for (int k = 0; k < naux; ++k)
-                        s1 += ixq[((long long)t.i1 * nphys + x) * ld_ixq + k] *
+                        s1 += (t.asel1 ? ixq2 : ixq)[((long long)t.i1 * nphys + x) * ld_ixq + k] *
                               q[((long long)k * no + t.j1) * ldq + t.a1 + c];
             }
             if (c < 8 * t.nb2) {
@@ -916,7 +920,7 @@ __global__ void k1_form_simple(const double* __restrict__ ixq, long long ld_ixq,
                 const int no = t.bsel2 ? nocc1 : nocc0, nv = t.bsel2 ? nvir1 : nvir0;
                 if (t.a2 + c < nv)
                     for (int k = 0; k < naux; ++k)
-                        s2 += ixq[((long long)t.i2 * nphys + x) * ld_ixq + k] *
+                        s2 += (t.asel2 ? ixq2 : ixq)[((long long)t.i2 * nphys + x) * ld_ixq + k] *
                               q[((long long)k * no + t.j2) * ldq + t.a2 + c];
             }
         }

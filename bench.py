@@ -325,8 +325,9 @@ def main():
     # occupied-sector call: o "occupied" poles, v "virtual"; virtual-sector call: roles swapped
     ixq_o = make((o, p, n), sc, 1); qja_o = make((n, o, v), sc, 2)
     ixq_v = make((v, p, n), sc, 3); qja_v = make((n, v, o), sc, 4)
-    e_o = torch.sort(torch.rand(o, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
-    e_v = torch.sort(torch.rand(v, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
+    ge = torch.Generator(device=dev); ge.manual_seed(5)       # (seeded: every rank must hold the same energies)
+    e_o = torch.sort(torch.rand(o, generator=ge, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
+    e_v = torch.sort(torch.rand(v, generator=ge, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
     eo_h, ev_h = e_o.cpu().numpy(), e_v.cpu().numpy()
     out = torch.zeros((2, 2, p, p), device=dev, dtype=torch.float64)   # [sector][vv|vev]
     kw = dict(os_factor=os_f, ss_factor=ss_f, naux=n)
