@@ -51,6 +51,7 @@ Options& default_options() {
         if (const char* e = getenv("AGF2_B200_COULOMB")) { o.coulomb = atoi(e) != 0; o.coulomb_auto = atoi(e) == 2; }
         if (const char* e = getenv("AGF2_B200_THIN")) o.thin_tiles = atoi(e) != 0;
         if (const char* e = getenv("AGF2_B200_DETERMINISTIC")) o.deterministic = atoi(e) != 0;
+        if (const char* e = getenv("AGF2_B200_VISITING_MB")) o.vis_bytes = (int64_t)atoll(e) << 20;
     }
     return o;
 }
@@ -124,6 +125,10 @@ int ctx_init(Ctx& c, int device) {
     CU_TRY(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c.ev_copy, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c.small_free, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CU_TRY(cudaEventCreateWithFlags(&c.vis_ready[b], cudaEventDisableTiming));
+        for (int s = 0; s < 2; ++s) CU_TRY(cudaEventCreateWithFlags(&c.vis_done[b][s], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -140,7 +145,9 @@ void ctx_free(Ctx* c) {
         for (int r = 0; r < 2; ++r)
             for (int b = 0; b < 2; ++b) if (c->W[r][b]) cudaFree(c->W[r][b]);
         for (int b = 0; b < 2; ++b) {
-            free_buf(c->E[b]); free_buf(c->partial[b]); free_buf(c->wq[b]);
+            free_buf(c->E[b]); free_buf(c->partial[b]); free_buf(c->wq[b]); free_buf(c->vis[b]);
+            if (c->vis_ready[b]) cudaEventDestroy(c->vis_ready[b]);
+            for (int s = 0; s < 2; ++s) if (c->vis_done[b][s]) cudaEventDestroy(c->vis_done[b][s]);
             if (c->d_t1[b]) cudaFree(c->d_t1[b]);
             if (c->h_t1[b]) cudaFreeHost(c->h_t1[b]);
             if (c->t1_free[b]) cudaEventDestroy(c->t1_free[b]);
@@ -418,48 +425,62 @@ struct SmallTables {
 
 struct SymTiles { const K2Tile* tiles; const int* cost; int ntiles; int total_cost; };
 
+int comm_allgather(Ctx& c, double* buf, int64_t count_per_rank, cudaStream_t st);
+
 // Coulomb part of the moments without forming a single Coulomb integral:
 //     sum_{i in slice} sum_{j,a} w_j X_ij X_ij^T (e_i + e_j - e_a)^n  =  sum_i ixq_i (e_i^n M0 + n M1) ixq_i^T ,
 //     M0 = sum_ja w_j q_ja q_ja^T ,  M1 = sum_ja w_j (e_j - e_a) q_ja q_ja^T      (naux x naux)
 // (k2_moment<false,true> on the (Q|ja) tensor), T = ixq_batch [M0 | M1] (general GEMM on the same pipeline) and
-// k2_moment<true,false>: vv += T0 ixq^T, vev += (e_i T0 + T1) ixq^T, upper triangle only.  With nparts GPUs each
-// one owns a block of rows Q' of M (and the matching K range of the last step).
-// M is kept as  Mt = [M0[Q', :] ; M1[Q', :]]  (2 nq_pad rows of ldm >= naux columns): the rows are the B operand
-// of the T GEMM (contraction index Q contiguous).
-int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other, int64_t nphys,
-                int64_t naux, int64_t istart, int64_t iend, double w_same_in, double w_same_out, double w_other,
-                int64_t part, int64_t nparts, double* S_vv, double* S_vev, int64_t p_pad, const SymTiles& sym,
-                SmallTables& small, const K2Tile* d_tm, const int* d_cm, int nt_m, int cost_m, cudaStream_t st)
+// k2_moment<true,false>: vv += T0 ixq^T, vev += (e_i T0 + T1) ixq^T, upper triangle only.
+// M is kept as  Mt = [M0[Q', :] ; M1[Q', :]]  (rows = the B operand of the T GEMM, contraction index Q contiguous).
+// Two ways to share the work between GPUs:
+//   replicated ixq (gather = false): part p of nparts owns the block of rows Q' of M and the matching K range of the
+//       last step, for ALL poles of the slice;
+//   pole-sharded ixq (gather = true): rank p builds its block of rows of M, an all-gather gives every rank the whole
+//       M, and each rank treats its own poles (ixq = the resident block of `iend - istart` poles, `pole_off` = global
+//       index of its first pole) with the full K range, one k2 launch per block of rows.
+int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, int64_t ixq_poles, const Spin& same, const Spin* other,
+                int64_t nphys, int64_t naux, int64_t istart, int64_t iend, double w_same_in, double w_same_out,
+                double w_other, int64_t part, int64_t nparts, bool gather, int64_t pole_off, double* S_vv, double* S_vev,
+                int64_t p_pad, const SymTiles& sym, const K2Tile* d_tm, const int* d_cm, int nt_m, int cost_m,
+                cudaStream_t st)
 {
     struct Pass { const Spin* sp; double w_in, w_out; };
     std::vector<Pass> passes;
-    const bool partial = istart > 0 || iend < same.nocc;
+    const bool partial = !gather && (istart > 0 || iend < same.nocc);
     if (w_same_in != 0.0 || (partial && w_same_out != 0.0)) passes.push_back({&same, w_same_in, w_same_out});
     if (other && w_other != 0.0) passes.push_back({other, w_other, w_other});
-    if (passes.empty() || iend <= istart || nt_m == 0) return 0;
+    if (passes.empty() || (iend <= istart && !gather)) return 0;
     const int64_t ntq = (naux + kTileM - 1) / kTileM;
-    const int64_t q_lo = ntq * part / nparts * kTileM;
-    const int64_t q_hi = std::min<int64_t>(naux, ntq * (part + 1) / nparts * kTileM);
-    if (q_hi <= q_lo) return 0;
-    const int64_t nq = q_hi - q_lo, nq_pad = rup(nq, kTileM);
+    auto blk_lo = [&](int64_t p) { return ntq * p / nparts * kTileM; };
+    auto blk_hi = [&](int64_t p) { return std::min<int64_t>(naux, ntq * (p + 1) / nparts * kTileM); };
+    const int64_t q_lo = blk_lo(part), q_hi = blk_hi(part);
+    const int64_t nq = std::max<int64_t>(0, q_hi - q_lo);
+    if (!gather && nq == 0) return 0;
+    // every block lives in a slot of nq_slot rows (gather: one slot per rank, equal sizes for the all-gather)
+    const int64_t nq_slot = gather ? (ntq + nparts - 1) / nparts * kTileM : rup(nq, kTileM);
+    const int64_t nslots = gather ? nparts : 1, my_slot = gather ? part : 0;
     const int64_t ldm = rup(naux, kTileN);
     const int msym = (nparts == 1) ? 1 : 0;   // the whole (symmetric) M: upper-triangle tiles, mirrored afterwards
+    const size_t slot_elems = (size_t)2 * nq_slot * ldm;
 
     // ---- M build ------------------------------------------------------------------------------------
-    if (int r = grow(c.Mbuf, (size_t)2 * nq_pad * ldm, false)) return r;
-    double* const Mt0 = c.Mbuf.p;
-    double* const Mt1 = c.Mbuf.p + nq_pad * ldm;
-    CU_TRY(cudaMemsetAsync(c.Mbuf.p, 0, (size_t)2 * nq_pad * ldm * 8, st));
+    if (int r = grow(c.Mbuf, slot_elems * nslots, false)) return r;
+    double* const Mt0 = c.Mbuf.p + slot_elems * my_slot;
+    double* const Mt1 = Mt0 + nq_slot * ldm;
+    CU_TRY(cudaMemsetAsync(Mt0, 0, slot_elems * 8, st));
     record(c, st, 2, true);
     for (const Pass& ps : passes) {
+        if (nq == 0 || nt_m == 0) break;
         const Spin& sp = *ps.sp;
         const int nki = (int)((sp.nvir + kKB - 1) / kKB);
         const int64_t kpad = (int64_t)nki * kKB;
         for (int b = 0; b < 2; ++b) if (int r = grow(c.wq[b], (size_t)(sp.nocc * kpad), false)) return r;
         dim3 gw((unsigned)((kpad + 127) / 128), (unsigned)sp.nocc);
         const bool is_same = ps.sp == &same;
+        const bool sliced = is_same && !gather;
         fill_m_weights<<<gw, 128, 0, st>>>(c.wq[0].p, c.wq[1].p, sp.ei_dev, sp.ea_dev, (int)sp.nvir, (int)kpad, ps.w_in,
-                                          ps.w_out, is_same ? (int)istart : 0, is_same ? (int)iend : (int)sp.nocc);
+                                          ps.w_out, sliced ? (int)istart : 0, sliced ? (int)iend : (int)sp.nocc);
         CU_TRY(cudaGetLastError());
         count_launch(c);
         K2Launch L;
@@ -485,19 +506,20 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         CU_TRY(cudaGetLastError());
         count_launch(c);
     }
+    if (gather && nparts > 1) if (int r = comm_allgather(c, c.Mbuf.p, (int64_t)slot_elems, st)) return r;
     record(c, st, 2, false);
+    if (iend <= istart) return 0;
 
     // ---- T = ixq_batch [M0 | M1]^T-rows, then the two moments ---------------------------------------------
-    const int64_t ldt = 2 * nq_pad;
+    const int64_t ldt = 2 * nq_slot * nslots;
     const int64_t per_pole = nphys * ldt;
     const int64_t nbi_max = std::max<int64_t>(1, std::min<int64_t>(64, (512ll << 20) / (per_pole * 8)));
-    const int nkq = (int)((nq + kKB - 1) / kKB);
-    const int64_t kpad = (int64_t)nkq * kKB;
+    const int64_t kpad = rup(gather ? nq_slot : nq, kKB);
     if (int r = grow(c.Tbuf, (size_t)(std::min<int64_t>(nbi_max, iend - istart) * per_pole), false)) return r;
     if (int r = grow(c.we, (size_t)(nbi_max * kpad), false)) return r;
     CUtensorMap mapIx;
     {
-        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)same.nocc};
+        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)ixq_poles};
         cuuint64_t sb[2] = {(cuuint64_t)ld_ixq * 8, (cuuint64_t)ld_ixq * 8 * (cuuint64_t)nphys};
         cuuint32_t bx[3] = {kKB, 64, 1};
         if (int r = make_map(c, &mapIx, ixq, 3, d, sb, bx)) return r;
@@ -507,31 +529,39 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         const int64_t nbi = std::min<int64_t>(nbi_max, iend - i0);
         Gemm g;
         g.a = ixq + i0 * nphys * ld_ixq; g.a_rows = nbi * nphys; g.lda = ld_ixq;
-        g.b = c.Mbuf.p; g.b_rows = 2 * nq_pad; g.ldb = ldm;
+        g.b = c.Mbuf.p; g.b_rows = 2 * nq_slot * nslots; g.ldb = ldm;
         g.k = naux;
         g.c = c.Tbuf.p; g.ldc = ldt;
         if (int r = run_gemm(c, g, st)) return r;
-        dim3 ge((unsigned)((kpad + 127) / 128), (unsigned)nbi);
-        fill_e_weights<<<ge, 128, 0, st>>>(c.we.p, same.ei_dev, (int)i0, (int)kpad);
-        CU_TRY(cudaGetLastError());
-        count_launch(c);
-        K2Launch L;
-        cuuint64_t d[3] = {(cuuint64_t)nq, (cuuint64_t)nphys, (cuuint64_t)nbi};
-        cuuint64_t sb[2] = {(cuuint64_t)ldt * 8, (cuuint64_t)ldt * 8 * (cuuint64_t)nphys};
-        cuuint32_t bx[3] = {kKB, 64, 1};
-        if (int r = make_map(c, &L.a0, c.Tbuf.p, 3, d, sb, bx)) return r;
-        if (int r = make_map(c, &L.a1, c.Tbuf.p + nq_pad, 3, d, sb, bx)) return r;
-        L.b = mapIx;
-        L.mode = 2;
-        L.total_cost = sym.total_cost;
-        K2Params p = k2_params();
-        p.w1 = c.we.p; p.tiles = sym.tiles; p.cost_prefix = sym.cost;
-        p.acc_vv = S_vv; p.acc_vev = S_vev; p.ldacc = p_pad;
-        p.ntiles = sym.ntiles; p.nk_inner = nkq; p.n_outer = (int)nbi;
-        p.b_k_off = (int)q_lo; p.b_outer_off = (int)i0;
-        p.rows_valid = (int)nphys; p.cols_valid = (int)nphys; p.sym = 1;
-        L.p = p;
-        if (int r = launch_k2(c, L, 0, st)) return r;
+        for (int64_t sl = 0; sl < nslots; ++sl) {
+            const int64_t s_lo = gather ? blk_lo(sl) : q_lo;
+            const int64_t s_nq = gather ? std::max<int64_t>(0, blk_hi(sl) - s_lo) : nq;
+            if (s_nq == 0) continue;
+            // weights e_i per (pole, K) column, laid out with this launch's K length per pole
+            const int64_t kp = rup(s_nq, kKB);
+            dim3 ge((unsigned)((kp + 127) / 128), (unsigned)nbi);
+            fill_e_weights<<<ge, 128, 0, st>>>(c.we.p, same.ei_dev, (int)(pole_off + i0), (int)kp);
+            CU_TRY(cudaGetLastError());
+            count_launch(c);
+            K2Launch L;
+            cuuint64_t d[3] = {(cuuint64_t)s_nq, (cuuint64_t)nphys, (cuuint64_t)nbi};
+            cuuint64_t sb[2] = {(cuuint64_t)ldt * 8, (cuuint64_t)ldt * 8 * (cuuint64_t)nphys};
+            cuuint32_t bx[3] = {kKB, 64, 1};
+            double* const t0 = c.Tbuf.p + 2 * nq_slot * sl;
+            if (int r = make_map(c, &L.a0, t0, 3, d, sb, bx)) return r;
+            if (int r = make_map(c, &L.a1, t0 + nq_slot, 3, d, sb, bx)) return r;
+            L.b = mapIx;
+            L.mode = 2;
+            L.total_cost = sym.total_cost;
+            K2Params p = k2_params();
+            p.w1 = c.we.p; p.tiles = sym.tiles; p.cost_prefix = sym.cost;
+            p.acc_vv = S_vv; p.acc_vev = S_vev; p.ldacc = p_pad;
+            p.ntiles = sym.ntiles; p.nk_inner = (int)((s_nq + kKB - 1) / kKB); p.n_outer = (int)nbi;
+            p.b_k_off = (int)s_lo; p.b_outer_off = (int)i0;
+            p.rows_valid = (int)nphys; p.cols_valid = (int)nphys; p.sym = 1;
+            L.p = p;
+            if (int r = launch_k2(c, L, 0, st)) return r;
+        }
     }
     record(c, st, 3, false);
     return 0;
@@ -541,18 +571,38 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
 struct Reduce { bool on = false; };
 
 int comm_allreduce_sum(Ctx& c, double* buf, int64_t count, cudaStream_t st);
+int comm_sendrecv(Ctx& c, const double* sendbuf, int64_t send_count, int dst, double* recvbuf, int64_t recv_count, int src,
+                  cudaStream_t st);
+
+// Pole-sharded build: `ixq` holds only the poles [shard_lo(o, rank, R), shard_lo(o, rank + 1, R)) of this rank of the
+// context's communicator; the other blocks visit over NVLink (see planner.h, shard_steps).
+struct Shard { int64_t rank, nranks; };
+// poles per visiting sub-block: what fits the "visiting_bytes" budget, at most the largest block
+int64_t shard_sub_block(const Options& o, int64_t nb_max, int64_t pole_elems) {
+    return std::max<int64_t>(1, std::min<int64_t>(nb_max, (o.vis_bytes / 8) / pole_elems));
+}
 
 // The whole moment build on device-resident inputs; vv/vev are accumulated into (+=).
 int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, const Spin* other,
                 const double* ei_same_host, const double* ei_other_host, int64_t nphys, int64_t naux,
                 int64_t istart, int64_t iend, double c_same, double s_same, double os_other, int64_t part,
-                int64_t nparts, double* vv, double* vev, cudaStream_t st, const PoleGate* gate, bool allreduce)
+                int64_t nparts, double* vv, double* vev, cudaStream_t st, const PoleGate* gate, bool allreduce,
+                const Shard* sh = nullptr)
 {
     const Options& opt = *c.opt;
     const int64_t o = same.nocc, v = same.nvir;
+    if (sh) {
+        if (other || gate) return fail(AGF2_B200_EINVAL, "pole-sharded builds: RHF, device-resident inputs only");
+        if (istart != 0 || iend != o) return fail(AGF2_B200_EINVAL, "pole-sharded builds cover the whole pole range");
+        if (o < sh->nranks) return fail(AGF2_B200_EINVAL, "pole-sharded builds need at least one pole per rank");
+        part = 0; nparts = 1;
+    }
+    // poles of the resident (ix|Q) operand, and the share of the Coulomb stage's M rows this GPU builds
+    const int64_t n_res = sh ? shard_lo(o, sh->rank + 1, sh->nranks) - shard_lo(o, sh->rank, sh->nranks) : o;
+    const int64_t m_part = sh ? sh->rank : part, m_nparts = sh ? sh->nranks : nparts;
     MomentPlan plan;
     if (int r = plan.init(plan_config(opt, c.num_sms), nphys, naux, o, v, other != nullptr, other ? other->nocc : 0,
-                          other ? other->nvir : 0, istart, iend, c_same, s_same, os_other, part, nparts))
+                          other ? other->nvir : 0, istart, iend, c_same, s_same, os_other, part, nparts, sh != nullptr))
         return fail(r, plan.error);
     if ((ld_ixq & 1) || ld_ixq < naux || (same.ld & 1) || same.ld < v || (other && ((other->ld & 1) || other->ld < other->nvir)))
         return fail(AGF2_B200_EINVAL, "leading dimensions must be even (16-byte TMA strides) and >= the row length");
@@ -600,7 +650,7 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
     // ---- TMA descriptors of the inputs ----------------------------------------------------------
     CUtensorMap mapA, mapB0, mapB1;
     {
-        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)o};
+        cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)n_res};
         cuuint64_t s[2] = {(cuuint64_t)ld_ixq * 8, (cuuint64_t)ld_ixq * 8 * (cuuint64_t)nphys};
         cuuint32_t b[3] = {kKB, kTileM, 1};
         if (int r = make_map(c, &mapA, ixq, 3, d, s, b)) return r;
@@ -640,10 +690,10 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
     for (const K2Tile& t : t2_all) cost_all.push_back(cost_all.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 0, 1));
     if (fact) {     // tiles of this part's block of M rows
         const int64_t ntq = (naux + kTileM - 1) / kTileM;
-        const int64_t q_lo = ntq * part / nparts * kTileM;
-        const int64_t q_hi = std::min<int64_t>(naux, ntq * (part + 1) / nparts * kTileM);
+        const int64_t q_lo = ntq * m_part / m_nparts * kTileM;
+        const int64_t q_hi = std::min<int64_t>(naux, ntq * (m_part + 1) / m_nparts * kTileM);
         const int64_t nq = std::max<int64_t>(0, q_hi - q_lo);
-        const int msym = (nparts == 1) ? 1 : 0;
+        const int msym = (m_nparts == 1) ? 1 : 0;
         const int nxm = (int)((nq + kTileM - 1) / kTileM), nym = (int)((naux + kTileN - 1) / kTileN);
         for (int xb = 0; xb < nxm; ++xb)
             for (int yb = 0; yb < nym; ++yb) {
@@ -777,17 +827,92 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         return 0;
     };
 
-    int rc = run_chunks(sym_items, true);
-    if (!rc) rc = run_chunks(asym_items, false);
+    int rc = 0;
+    if (!sh) {
+        rc = run_chunks(sym_items, true);
+        if (!rc) rc = run_chunks(asym_items, false);
+    } else {
+        // ---- pole-sharded pair loop: own block first, then the visiting sub-blocks of the other ranks' blocks,
+        // each received on the copy stream (NCCL send/recv over NVLink) while the previous one is being worked on
+        const int64_t R = sh->nranks, rk = sh->rank;
+        const int64_t pole_elems = nphys * ld_ixq;
+        int64_t nb_max = 0;
+        for (int64_t r = 0; r < R; ++r) nb_max = std::max(nb_max, shard_lo(o, r + 1, R) - shard_lo(o, r, R));
+        const int64_t sb = shard_sub_block(*c.opt, nb_max, pole_elems);
+        const std::vector<ShardStep> steps = shard_steps(o, rk, R, sb, c.opt->shard_limit);
+        CUtensorMap mapVis[2];
+        if (R > 1) {
+            for (int b = 0; b < 2; ++b) {
+                if (int r = grow(c.vis[b], (size_t)(sb * pole_elems), false)) return r;
+                cuuint64_t d[3] = {(cuuint64_t)naux, (cuuint64_t)nphys, (cuuint64_t)sb};
+                cuuint64_t s[2] = {(cuuint64_t)ld_ixq * 8, (cuuint64_t)ld_ixq * 8 * (cuuint64_t)nphys};
+                cuuint32_t bx[3] = {kKB, kTileM, 1};
+                if (int r = make_map(c, &mapVis[b], c.vis[b].p, 3, d, s, bx)) return r;
+            }
+        }
+        // the resident block must be complete before a peer reads it: order the copy stream behind the caller's
+        CU_TRY(cudaEventRecord(c.ev_copy, st));
+        CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.ev_copy, 0));
+        std::vector<size_t> xfer;          // indices of the steps that move data, in order
+        for (size_t q = 0; q < steps.size(); ++q) if (steps[q].recv || steps[q].send) xfer.push_back(q);
+        bool used_buf[2] = {false, false};
+        auto enqueue_transfer = [&](size_t x) -> int {
+            const ShardStep& s = steps[xfer[x]];
+            const int b = (int)(x & 1);
+            if (used_buf[b])       // the previous tenant of this buffer has been consumed (both compute streams)
+                for (int q = 0; q < nsets; ++q) CU_TRY(cudaStreamWaitEvent(c.copy_stream, c.vis_done[b][q], 0));
+            if (int r = comm_sendrecv(c, s.send ? ixq + (s.send_lo - shard_lo(o, rk, R)) * pole_elems : nullptr,
+                                      s.send ? (s.send_hi - s.send_lo) * pole_elems : 0, s.dst,
+                                      s.recv ? c.vis[b].p : nullptr, s.recv ? (s.vis_hi - s.vis_lo) * pole_elems : 0, s.src,
+                                      c.copy_stream))
+                return r;
+            CU_TRY(cudaEventRecord(c.vis_ready[b], c.copy_stream));
+            return 0;
+        };
+        if (!xfer.empty()) rc = enqueue_transfer(0);
+        size_t x = 0;                      // next transfer step to be consumed
+        for (size_t q = 0; q < steps.size() && !rc; ++q) {
+            const ShardStep& s = steps[q];
+            const bool moves = s.recv || s.send;
+            int b = -1;
+            if (moves) {
+                b = (int)(x & 1);
+                if (x + 1 < xfer.size()) rc = enqueue_transfer(x + 1);
+                ++x;
+                if (rc) break;
+            }
+            if (s.vis_hi > s.vis_lo) {
+                plan.set_shard_step(rk, R, s);
+                if (s.recv) {
+                    CU_TRY(cudaStreamWaitEvent(st, c.vis_ready[b], 0));
+                    if (overlap) CU_TRY(cudaStreamWaitEvent(c.stream2, c.vis_ready[b], 0));
+                    mapA2 = &mapVis[b];
+                    ixq2 = c.vis[b].p;
+                }
+                c.last_plan[1] += (int64_t)plan.sym_items.size();
+                rc = run_chunks(plan.sym_items, true);
+            }
+            if (moves && s.recv) {
+                CU_TRY(cudaEventRecord(c.vis_done[b][0], st));
+                if (overlap) CU_TRY(cudaEventRecord(c.vis_done[b][1], c.stream2));
+                used_buf[b] = true;
+            }
+        }
+    }
     if (!rc && fact) {
         // host-pointer API: every pole of the slice must have landed
         if (gate) rc = gate_wait(gate, (int)(iend - istart) - 1, st);
         // weights of the Coulomb-type terms: same-spin tensor (c - s) [+ s for j outside the slice], other spin os
         if (!rc) {
             const SymTiles symt{d_t2_sym, d_cost_sym, (int)t2_sym.size(), cost_sym.back()};
-            rc = run_coulomb(c, ixq, ld_ixq, same, other, nphys, naux, istart, iend, c_same - s_same, c_same, os_other,
-                             part, nparts, c.acc.p, c.acc.p + acc_n, p_pad, symt, small, d_t2_m, d_cost_m,
-                             (int)t2_m.size(), cost_m.back(), st);
+            if (sh)
+                rc = run_coulomb(c, ixq, ld_ixq, n_res, same, nullptr, nphys, naux, 0, n_res, c_same - s_same, c_same, 0.0,
+                                 sh->rank, sh->nranks, true, shard_lo(o, sh->rank, sh->nranks), c.acc.p, c.acc.p + acc_n,
+                                 p_pad, symt, d_t2_m, d_cost_m, (int)t2_m.size(), cost_m.back(), st);
+            else
+                rc = run_coulomb(c, ixq, ld_ixq, o, same, other, nphys, naux, istart, iend, c_same - s_same, c_same,
+                                 os_other, part, nparts, false, 0, c.acc.p, c.acc.p + acc_n, p_pad, symt, d_t2_m, d_cost_m,
+                                 (int)t2_m.size(), cost_m.back(), st);
         }
     }
     // join the second chain (also on error paths: nothing may be left in flight behind the caller's back)

@@ -104,6 +104,23 @@ int comm_allgather(Ctx& c, double* buf, int64_t count_per_rank, cudaStream_t st)
     return 0;
 }
 
+// One step of the pole-block exchange: send `send_count` doubles to rank dst and receive `recv_count` from rank src
+// (either may be empty), as one NCCL group on `st`.
+int comm_sendrecv(Ctx& c, const double* sendbuf, int64_t send_count, int dst, double* recvbuf, int64_t recv_count, int src,
+                  cudaStream_t st) {
+    if (send_count <= 0 && recv_count <= 0) return 0;
+    if (!c.comm) return fail(AGF2_B200_ECOMM, "context has no communicator");
+    NCCL_TRY(g_nccl.GroupStart());
+    int r1 = 0, r2 = 0;
+    if (send_count > 0) r1 = g_nccl.Send(sendbuf, (size_t)send_count, kNcclDouble, dst, c.comm, st);
+    if (recv_count > 0) r2 = g_nccl.Recv(recvbuf, (size_t)recv_count, kNcclDouble, src, c.comm, st);
+    NCCL_TRY(g_nccl.GroupEnd());
+    NCCL_TRY(r1);
+    NCCL_TRY(r2);
+    if (send_count > 0) c.last_comm_bytes[2] += send_count * 8;
+    return 0;
+}
+
 Ctx* resolve_ctx(agf2_b200_ctx* ctx, int* status) {
     *status = 0;
     if (ctx) return ctx;

@@ -47,6 +47,8 @@ struct Options {
     bool coulomb_auto = true;          // ... and chosen per call by a flop estimate
     bool deterministic = true;         // stream-K partial tiles summed in a fixed order (k2_fixup)
     bool profile = true;               // CUDA events around every launch (agf2_b200_last_stage_ms)
+    int64_t vis_bytes = 2ll << 30;     // pole-sharded builds: size of one visiting sub-block of (ix|Q) (two are kept)
+    int64_t shard_limit = 0;           // > 0: only the first `shard_limit` sub-blocks of every ring step (benchmark sample)
 };
 Options& default_options();
 
@@ -84,6 +86,10 @@ struct agf2_b200_ctx {
     void* d_gemm = nullptr; size_t d_gemm_cap = 0;      // tile list + prefix of general GEMM launches (device-generated)
     // Coulomb factorisation scratch
     agf2::DevBuf Mbuf, Tbuf, wq[2], we;
+    // pole-sharded builds: double-buffered visiting sub-blocks of (ix|Q) and their events
+    agf2::DevBuf vis[2];
+    cudaEvent_t vis_ready[2] = {nullptr, nullptr};          // sub-block has landed (copy stream)
+    cudaEvent_t vis_done[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [buffer][compute stream]: last reader finished
     // host-pointer API staging
     agf2::DevBuf stage[8];
     double* h_result = nullptr; size_t h_result_cap = 0;   // pinned D2H staging of [vv | vev]
@@ -100,7 +106,8 @@ struct agf2_b200_ctx {
     int64_t last_plan[6] = {0, 0, 0, 0, 0, 0};   // factorised, PAIR, DIAG, OS, ASYM items, k1_form launches
     double last_ms[4] = {0, 0, 0, 0};            // k1_form, k2_moment (pairs), M build, Coulomb step (GEMM + k2)
     double flops[3] = {0, 0, 0};                 // executed FP64 tensor flops since the last reset: k1_form, k2_moment, GEMM
-    int64_t last_comm_bytes[2] = {0, 0};         // bytes this rank sent over NVLink in the last call: all-gather, all-reduce
+    int64_t last_comm_bytes[3] = {0, 0, 0};      // bytes this rank sent over NVLink in the last call: all-gather, all-reduce,
+                                                 // point-to-point (visiting pole blocks of a pole-sharded build)
 };
 
 namespace agf2 {

@@ -180,7 +180,7 @@ int host_rhf(Ctx& c, const double* ixq, const double* qja, const double* ei, con
     cudaStream_t st = c.stream;
     const bool multi = comm && c.nranks > 1;
     if (multi) { part = c.rank; nparts = c.nranks; }
-    c.last_comm_bytes[0] = c.last_comm_bytes[1] = 0;
+    c.last_comm_bytes[0] = c.last_comm_bytes[1] = c.last_comm_bytes[2] = 0;
     int64_t ld_ixq, ld_qja, ld1;
     // qja travels on the copy stream too: with a communicator its all-gather must precede the uploader's on every rank
     if (int r = stage_in(c, 1, qja, naux * nocc, nvir, &ld_qja, multi, c.copy_stream)) return r;   // (naux*nocc) rows of nvir
@@ -217,7 +217,7 @@ int host_uhf(Ctx& c, const double* ixq_a, const double* qja_a, const double* qja
     cudaStream_t st = c.stream;
     const bool multi = comm && c.nranks > 1;
     if (multi) { part = c.rank; nparts = c.nranks; }
-    c.last_comm_bytes[0] = c.last_comm_bytes[1] = 0;
+    c.last_comm_bytes[0] = c.last_comm_bytes[1] = c.last_comm_bytes[2] = 0;
     const bool has_b = nocc_b > 0 && nvir_b > 0;
     int64_t ld_ixq, ld_qa, ld_qb = 2, ld1;
     if (int r = stage_in(c, 1, qja_a, naux * nocc_a, nvir_a, &ld_qa, multi, c.copy_stream)) return r;
@@ -326,6 +326,10 @@ static int set_option(Options& o, const char* name, int64_t value) {
     else if (n == "thin_tiles") o.thin_tiles = value != 0;
     else if (n == "deterministic") o.deterministic = value != 0;
     else if (n == "profile") o.profile = value != 0;
+    else if (n == "visiting_bytes") {
+        if (value < 1) return fail(AGF2_B200_EINVAL, "visiting_bytes must be positive");
+        o.vis_bytes = value;
+    } else if (n == "shard_step_limit") o.shard_limit = value < 0 ? 0 : value;
     else if (n == "coulomb_factorization") {
         if (value < 0 || value > 2) return fail(AGF2_B200_EINVAL, "mode must be 0 (off), 1 (always) or 2 (automatic)");
         o.coulomb = value != 0;
@@ -382,6 +386,51 @@ int agf2_b200_ctx_last_comm_bytes(agf2_b200_ctx* ctx, int64_t* bytes2) {
     if (!c) return s;
     bytes2[0] = c->last_comm_bytes[0];
     bytes2[1] = c->last_comm_bytes[1];
+    return 0;
+}
+
+// sub-block size (poles) a pole-sharded build of this shape uses on this context
+int64_t agf2_b200_ctx_shard_sub_block(agf2_b200_ctx* ctx, int64_t nocc, int64_t nphys, int64_t ld_ixq, int64_t nranks) {
+    int s;
+    Ctx* c = resolve_ctx(ctx, &s);
+    if (!c || nranks < 1 || nocc < nranks) return -1;
+    int64_t nb_max = 0;
+    for (int64_t r = 0; r < nranks; ++r) nb_max = std::max(nb_max, shard_lo(nocc, r + 1, nranks) - shard_lo(nocc, r, nranks));
+    return shard_sub_block(*c->opt, nb_max, nphys * ld_ixq);
+}
+
+int64_t agf2_b200_ctx_last_p2p_bytes(agf2_b200_ctx* ctx) {
+    int s;
+    Ctx* c = resolve_ctx(ctx, &s);
+    return c ? c->last_comm_bytes[2] : -1;
+}
+
+int agf2_b200_pole_block(int64_t nocc, int64_t rank, int64_t nranks, int64_t* lo, int64_t* hi) {
+    if (nocc < 0 || nranks < 1 || rank < 0 || rank >= nranks || !lo || !hi) return fail(AGF2_B200_EINVAL, "bad argument");
+    *lo = shard_lo(nocc, rank, nranks);
+    *hi = shard_lo(nocc, rank + 1, nranks);
+    return 0;
+}
+
+// Host-only replay of the pole-sharded schedule of all ranks (tests): cover[i * nocc + j] += 1 for every pair item
+// (i, j) any rank forms, stats[2 r] = pairs of rank r, stats[2 r + 1] = poles rank r sends.
+int agf2_b200_shard_cover(int64_t nocc, int64_t nranks, int64_t sub_block, int64_t limit, int64_t* cover, int64_t* stats) {
+    if (nocc < nranks || nranks < 1 || sub_block < 1 || !cover || !stats) return fail(AGF2_B200_EINVAL, "bad argument");
+    for (int64_t r = 0; r < nranks; ++r) {
+        MomentPlan plan;
+        if (int rc = plan.init(plan_config(default_options(), 148), 8, 8, nocc, 8, false, 0, 0, 0, nocc, 2.0, 1.0, 0.0, 0, 1, true))
+            return fail(rc, plan.error);
+        for (const ShardStep& s : shard_steps(nocc, r, nranks, sub_block, limit)) {
+            if (s.send) stats[2 * r + 1] += s.send_hi - s.send_lo;
+            if (s.vis_hi <= s.vis_lo) continue;
+            plan.set_shard_step(r, nranks, s);
+            for (const Item& it : plan.sym_items) {
+                const int64_t a = std::max(it.i, it.j), b = std::min(it.i, it.j);
+                cover[a * nocc + b] += 1;
+                stats[2 * r] += 1;
+            }
+        }
+    }
     return 0;
 }
 
@@ -497,9 +546,38 @@ int agf2_b200_ctx_moments_rhf_dev(agf2_b200_ctx* ctx, const double* ixq, int64_t
     if (!c) return s;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard guard(c->device);
-    c->last_comm_bytes[0] = c->last_comm_bytes[1] = 0;
+    c->last_comm_bytes[0] = c->last_comm_bytes[1] = c->last_comm_bytes[2] = 0;
     return moments_rhf_impl(*c, ixq, ld_ixq, qja, ld_qja, ei, ea, ei_host, nphys, nocc, nvir, naux, istart, iend, os_factor,
                             ss_factor, c->rank, c->nranks, vv, vev, (cudaStream_t)stream, sync, nullptr, true);
+}
+
+int agf2_b200_ctx_moments_rhf_dev_sharded(agf2_b200_ctx* ctx, const double* ixq_block, int64_t ld_ixq, const double* qja,
+                                          int64_t ld_qja, const double* ei, const double* ea, const double* ei_host,
+                                          int64_t nphys, int64_t nocc, int64_t nvir, int64_t naux, double os_factor,
+                                          double ss_factor, double* vv, double* vev, void* stream, int sync)
+{
+    int s;
+    Ctx* c = resolve_ctx(ctx, &s);
+    if (!c) return s;
+    if (!ixq_block || !qja || !ei || !ea || !vv || !vev) return fail(AGF2_B200_EINVAL, "null pointer");
+    if (nocc <= 0) return fail(AGF2_B200_EINVAL, "empty dimension");
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    c->last_comm_bytes[0] = c->last_comm_bytes[1] = c->last_comm_bytes[2] = 0;
+    if (int r = grow_pinned(c->h_energy, c->h_energy_cap, (size_t)nocc)) return r;
+    const double* ei_h = nullptr;
+    bool need_sync = false;
+    if (int r = host_energies(*c, ei, ei_host, nocc, 0, &ei_h, st, &need_sync)) return r;
+    if (need_sync) CU_TRY(cudaStreamSynchronize(st));
+    Spin same;
+    same.qja = qja; same.ld = ld_qja; same.nocc = nocc; same.nvir = nvir; same.ea_dev = ea; same.ei_dev = ei;
+    const Shard sh{c->rank, c->nranks};
+    if (int r = run_moments(*c, ixq_block, ld_ixq, same, nullptr, ei_h, nullptr, nphys, naux, 0, nocc,
+                            os_factor + ss_factor, ss_factor, 0.0, 0, 1, vv, vev, st, nullptr, true, &sh))
+        return r;
+    if (sync) return finish_profile(*c, st);
+    return 0;
 }
 
 int agf2_b200_ctx_moments_uhf_dev(agf2_b200_ctx* ctx, const double* ixq_a, int64_t ld_ixq, const double* qja_a,
@@ -514,7 +592,7 @@ int agf2_b200_ctx_moments_uhf_dev(agf2_b200_ctx* ctx, const double* ixq_a, int64
     if (!c) return s;
     std::lock_guard<std::mutex> lk(c->mu);
     DeviceGuard guard(c->device);
-    c->last_comm_bytes[0] = c->last_comm_bytes[1] = 0;
+    c->last_comm_bytes[0] = c->last_comm_bytes[1] = c->last_comm_bytes[2] = 0;
     return moments_uhf_impl(*c, ixq_a, ld_ixq, qja_a, ld_qja_a, qja_b, ld_qja_b, ei_a, ei_b, ea_a, ea_b, ei_a_host,
                             ei_b_host, nphys, nocc_a, nocc_b, nvir_a, nvir_b, naux, istart, iend, os_factor, ss_factor,
                             c->rank, c->nranks, vv, vev, (cudaStream_t)stream, sync, nullptr, true);

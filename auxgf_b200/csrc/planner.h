@@ -75,6 +75,45 @@ inline int pick_chunk_items(const std::vector<double>& item_tiles, int n_max, in
     return best_n;
 }
 
+// ---- pole-sharded builds --------------------------------------------------------------------------
+// (ix|Q) is split over the R GPUs by contiguous pole blocks, block r = [o r / R, o (r+1) / R); (Q|ja) is replicated.
+// Rank r forms every pair inside its own block (step t = 0) and, for t = 1 .. R-1, the pairs (i in its block, j in
+// the block of rank src = r - t) whose index sum has the parity assigned to it -- the lower rank of a block pair
+// takes the even sums, the higher one the odd sums -- while the poles of block src visit in sub-blocks of `sb`
+// poles (sent by their owner over NVLink, double-buffered under the pair loop).  Every unordered pair is formed
+// exactly once and every rank does the same amount of work without any rank holding more than its own block plus
+// two sub-blocks.  Replaces the replicated inputs of auxgf/mpi/agf2/optragf2.py:370-374 for shapes whose (ix|Q)
+// does not fit one GPU.
+inline int64_t shard_lo(int64_t o, int64_t r, int64_t R) { return o * r / R; }
+
+struct ShardStep {
+    int t = 0, k = 0;             // ring step, sub-block index within the step
+    int src = 0, dst = 0;         // owner of the visiting block, receiver of this rank's block
+    int64_t vis_lo = 0, vis_hi = 0;     // visiting poles (global indices; t = 0: a sub-range of the own block)
+    int64_t send_lo = 0, send_hi = 0;   // own poles sent to dst in this step (empty: nothing to send)
+    bool recv = false, send = false;
+};
+
+// limit > 0: only the first `limit` sub-blocks of every ring step (a benchmark sample of a build; the same on every rank)
+inline std::vector<ShardStep> shard_steps(int64_t o, int64_t rank, int64_t R, int64_t sb, int64_t limit = 0) {
+    std::vector<ShardStep> out;
+    const int64_t my_lo = shard_lo(o, rank, R), my_hi = shard_lo(o, rank + 1, R);
+    for (int64_t t = 0; t < R; ++t) {
+        const int64_t src = (rank - t + R) % R, dst = (rank + t) % R;
+        const int64_t s_lo = shard_lo(o, src, R), s_hi = shard_lo(o, src + 1, R);
+        const int64_t k_recv = (s_hi - s_lo + sb - 1) / sb, k_send = t ? (my_hi - my_lo + sb - 1) / sb : 0;
+        for (int64_t k = 0; k < std::max(k_recv, k_send); ++k) {
+            if (limit > 0 && k >= limit) break;
+            ShardStep s;
+            s.t = (int)t; s.k = (int)k; s.src = (int)src; s.dst = (int)dst;
+            if (k < k_recv) { s.vis_lo = s_lo + k * sb; s.vis_hi = std::min(s_hi, s.vis_lo + sb); s.recv = t > 0; }
+            if (k < k_send) { s.send_lo = my_lo + k * sb; s.send_hi = std::min(my_hi, s.send_lo + sb); s.send = true; }
+            out.push_back(s);
+        }
+    }
+    return out;
+}
+
 struct PlanConfig {
     int64_t ws_bytes = 40ll << 20;   // workspace per ring buffer
     int num_sms = 148;
@@ -101,12 +140,16 @@ struct MomentPlan {
     std::vector<std::pair<int, int>> blk_same, blk_other;
     int chunk_items[4] = {0, 0, 0, 0};   // items per chunk, per kind (0 = not yet chosen)
     const char* error = "";
+    // pole-sharded builds: resident block [res_lo, res_hi) (operand map 0, indexed from res_lo), visiting poles
+    // [vis_lo, vis_hi) (operand map 1, indexed from vis_lo)
+    bool sharded = false;
+    int64_t res_lo = 0, res_hi = 0, vis_lo = 0, vis_hi = 0;
 
     // Same-spin tensor (o poles x v), optional other-spin tensor (ob x vb); coefficients: vv = c C_same - s Xc_same
     // + os_other C_other.  Returns 0, or 3 (AGF2_B200_EINVAL) with `error` set.
     int init(const PlanConfig& config, int64_t nphys_, int64_t naux_, int64_t o_, int64_t v_, bool has_other_,
              int64_t ob_, int64_t vb_, int64_t istart_, int64_t iend_, double c_same_, double s_same_,
-             double os_other_, int64_t part_, int64_t nparts_)
+             double os_other_, int64_t part_, int64_t nparts_, bool sharded_ = false)
     {
         cfg = config;
         nphys = nphys_; naux = naux_; o = o_; v = v_; has_other = has_other_; ob = has_other_ ? ob_ : 0;
@@ -146,6 +189,11 @@ struct MomentPlan {
             const double fwork = (nparts == 1 ? 0.5 : 1.0) * 4.0 * N * N * mcols + ni * (4.0 * P * N * N + k2col * N);
             fact = mcols > 0.0 && fwork < 0.95 * direct;
         }
+        sharded = sharded_;
+        if (sharded) {     // the pair loop only carries the exchange-type term; items come from set_shard_step()
+            if (cfg.simple) { error = "pole-sharded builds need the tensor-core kernels (simple_kernels = 0)"; return 3; }
+            fact = true;
+        }
         ca = fact ? std::sqrt(s_same) : std::sqrt(0.5 * (c_same + s_same));
         cs = fact ? 0.0 : std::sqrt(0.5 * (c_same - s_same));
         cd = fact ? 0.0 : std::sqrt(c_same - s_same);
@@ -163,7 +211,7 @@ struct MomentPlan {
         asym_items.clear();
         int64_t n_diag = 0, n_pair = 0, n_os = 0, n_asym = 0;
         std::vector<Item> diag_items, os_items;
-        for (int64_t i = istart; i < iend; ++i) {
+        for (int64_t i = istart; i < iend && !sharded; ++i) {
             if (cd != 0.0 && (n_diag++ % nparts) == part) diag_items.push_back({0, (int)i, (int)i});
             if (ca != 0.0 || cs != 0.0)
                 for (int64_t j = istart; j < i; ++j)
@@ -181,6 +229,28 @@ struct MomentPlan {
         blk_other = split_blocks(vbpad);
         for (int k = 0; k < 4; ++k) chunk_items[k] = 0;
         return 0;
+    }
+
+    // Pole-sharded build: the PAIR items of one step of shard_steps() for `rank` of R (replaces sym_items).
+    void set_shard_step(int64_t rank, int64_t R, const ShardStep& s) {
+        sharded = true;
+        res_lo = shard_lo(o, rank, R); res_hi = shard_lo(o, rank + 1, R);
+        vis_lo = s.vis_lo; vis_hi = s.vis_hi;
+        sym_items.clear();
+        asym_items.clear();
+        if (ca == 0.0) return;
+        const int64_t want = rank < s.src ? 0 : 1;     // parity of i + j this rank takes of the block pair
+        for (int64_t i = res_lo; i < res_hi; ++i)
+            for (int64_t j = vis_lo; j < vis_hi; ++j) {
+                if (s.t == 0 ? (j >= i) : (((i + j) & 1) != want)) continue;
+                sym_items.push_back({1, (int)i, (int)j});
+            }
+    }
+    // operand index of pole `pole` of the (ix|Q) tensor: resident map (asel 0) or visiting map (asel 1)
+    void localize(int& pole, int& asel) const {
+        if (!sharded) return;
+        if (pole >= res_lo && pole < res_hi) { pole -= (int)res_lo; asel = 0; }
+        else { pole -= (int)vis_lo; asel = 1; }
     }
 
     // thin-tile mapping of the last x-block (k1_mainloop_thin): number of valid 8-row blocks, 0 = full tile
@@ -274,6 +344,8 @@ struct MomentPlan {
                             t.ws2 = 1; t.p21 = asym_c; t.p22 = -s_same;   // (p21 = 0: out2 width falls back to nb2 == nb1)
                         }
                         t.mbv = thin_mbv(xb, t.nb1, t.nb2);
+                        localize(t.i1, t.asel1);
+                        localize(t.i2, t.asel2);
                         tiles.push_back(t);
                     }
                 }

@@ -43,6 +43,9 @@ SYMBOLS = [
     "agf2_b200_ctx_moments_rhf_dev", "agf2_b200_ctx_moments_uhf_dev", "agf2_b200_ctx_build_part_loop_rhf",
     "agf2_b200_ctx_build_part_loop_uhf", "agf2_b200_host_register", "agf2_b200_host_unregister", "agf2_b200_ctx_gemm",
     "agf2_b200_ctx_flop_counters",
+    # pole-sharded builds
+    "agf2_b200_pole_block", "agf2_b200_ctx_moments_rhf_dev_sharded", "agf2_b200_ctx_last_p2p_bytes",
+    "agf2_b200_shard_cover", "agf2_b200_ctx_shard_sub_block",
 ]
 
 
@@ -114,6 +117,14 @@ _libagf2.agf2_b200_ctx_build_part_loop_uhf.argtypes = [_vp, _in2, _in2, _in2, _i
     [_dbl, _dbl, _out2, _out2]
 _libagf2.agf2_b200_ctx_gemm.argtypes = [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp]
 _libagf2.agf2_b200_ctx_flop_counters.argtypes = [_vp, ctypes.POINTER(_dbl), ctypes.c_int]
+_libagf2.agf2_b200_pole_block.argtypes = [_i64, _i64, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
+_libagf2.agf2_b200_ctx_moments_rhf_dev_sharded.argtypes = [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp] + [_i64] * 4 + \
+    [_dbl, _dbl, _vp, _vp, _vp, ctypes.c_int]
+_libagf2.agf2_b200_ctx_last_p2p_bytes.restype = _i64
+_libagf2.agf2_b200_ctx_last_p2p_bytes.argtypes = [_vp]
+_libagf2.agf2_b200_shard_cover.argtypes = [_i64, _i64, _i64, _i64, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]
+_libagf2.agf2_b200_ctx_shard_sub_block.restype = _i64
+_libagf2.agf2_b200_ctx_shard_sub_block.argtypes = [_vp, _i64, _i64, _i64, _i64]
 _libagf2.agf2_b200_host_register.argtypes = [_vp, _i64]
 _libagf2.agf2_b200_host_unregister.argtypes = [_vp]
 # the reference's own void symbols (drop-in ABI; argtypes as auxgf/lib/agf2.py:28-60)
@@ -411,6 +422,60 @@ def moments_rhf_dev(ixq, qja, ei, ea, istart=0, iend=None, os_factor=1.0, ss_fac
                                                  ea.data_ptr(), nphys, nocc, nvir, naux, istart, iend, os_factor,
                                                  ss_factor, part, nparts, vv.data_ptr(), vev.data_ptr(), stream,
                                                  1 if sync else 0))
+    return vv, vev
+
+
+def pole_block(nocc, rank, size):
+    """[lo, hi): the poles of (ix|Q) that rank ``rank`` of ``size`` holds in a pole-sharded build."""
+    lo, hi = _i64(0), _i64(0)
+    check(_libagf2.agf2_b200_pole_block(nocc, rank, size, ctypes.byref(lo), ctypes.byref(hi)))
+    return int(lo.value), int(hi.value)
+
+
+def shard_sub_block(nocc, nphys, ld_ixq, nranks, ctx=None):
+    """Poles per visiting sub-block of a pole-sharded build of this shape (``visiting_bytes`` option)."""
+    return int(_libagf2.agf2_b200_ctx_shard_sub_block(ctx, nocc, nphys, ld_ixq, nranks))
+
+
+def shard_cover(nocc, nranks, sub_block, limit=0):
+    """Host-only replay of the pole-sharded pair schedule: (cover, stats) with cover[i, j] = how often the ranks form
+    the unordered pair {i, j} (i > j; must be exactly 1) and stats = per-rank (pairs, poles sent), shape (nranks, 2)."""
+    cover = np.zeros((nocc, nocc), dtype=np.int64)
+    stats = np.zeros((nranks, 2), dtype=np.int64)
+    check(_libagf2.agf2_b200_shard_cover(nocc, nranks, sub_block, limit, cover.ctypes.data_as(ctypes.POINTER(_i64)),
+                                         stats.ctypes.data_as(ctypes.POINTER(_i64))))
+    return cover, stats
+
+
+def last_p2p_bytes(ctx=None):
+    """Bytes this rank sent point-to-point over NVLink (visiting pole blocks) in the last pole-sharded build."""
+    return int(_libagf2.agf2_b200_ctx_last_p2p_bytes(ctx))
+
+
+def moments_rhf_dev_sharded(ixq_block, qja, ei, ea, os_factor=1.0, ss_factor=1.0, vv=None, vev=None, sync=True,
+                            naux=None, ei_host=None, ctx=None):
+    """Pole-sharded device-resident build on the library's communicator: ``ixq_block`` holds only this rank's poles
+    ``pole_block(nocc, rank, size)`` of (ix|Q) -- (hi - lo, nphys, ld >= naux) -- while ``qja``, ``ei``, ``ea`` are
+    complete on every rank; the other ranks' poles visit over NVLink inside the call and one all-reduce gives every
+    rank the full (vv, vev).  For shapes whose (ix|Q) does not fit one GPU (BASELINE configs[4])."""
+    import torch
+    _check_dev(ixq_block, "ixq_block"); _check_dev(qja, "qja"); _check_dev(ei, "ei"); _check_dev(ea, "ea")
+    nloc, nphys, ld_ixq = ixq_block.shape
+    naux = ld_ixq if naux is None else naux
+    nocc, nvir, ld_qja = ei.numel(), ea.numel(), qja.shape[2]
+    rank, size = comm_info(ctx)
+    lo, hi = pole_block(nocc, rank, size)
+    assert nloc == hi - lo, "ixq_block must hold the poles [%d, %d) of this rank" % (lo, hi)
+    assert qja.shape[0] == naux and qja.shape[1] == nocc and ld_qja >= nvir
+    if vv is None:
+        vv = torch.zeros((nphys, nphys), dtype=torch.float64, device=qja.device)
+    if vev is None:
+        vev = torch.zeros((nphys, nphys), dtype=torch.float64, device=qja.device)
+    eh = None if ei_host is None else _c(ei_host, 1)
+    check(_libagf2.agf2_b200_ctx_moments_rhf_dev_sharded(
+        ctx, ixq_block.data_ptr(), ld_ixq, qja.data_ptr(), ld_qja, ei.data_ptr(), ea.data_ptr(),
+        None if eh is None else eh.ctypes.data, nphys, nocc, nvir, naux, os_factor, ss_factor, vv.data_ptr(),
+        vev.data_ptr(), torch.cuda.current_stream(qja.device).cuda_stream, 1 if sync else 0))
     return vv, vev
 
 

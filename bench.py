@@ -231,6 +231,59 @@ def reference_arm(args, o, v, n, p):
     return 0
 
 
+def projection_parity(torch, lib, dev, world, rank, sample_limit, sectors, n, p, os_f, ss_f):
+    """Size-independent check of a (pole-sharded) build against an independent evaluation: for a random vector u,
+        u^T vv u = (os+ss) sum_ija z_ija^2 - ss sum_ija z_ija z_jia ,   z_ija = sum_Q (u^T ixq_i)[Q] qja[Q, j, a]
+    (and the same with the weights e_i + e_j - e_a for vev) costs 1/nphys of the build and needs no integral block: the
+    projected (ix|Q) of every rank's poles is all-reduced, z comes from one library-independent torch.matmul (cuBLAS).
+    With a sampled virtual-sector call the exchange-type sum runs over exactly the pairs the sample formed (replayed on
+    the host by agf2_b200_shard_cover)."""
+    diffs = []
+    for k, (ixq_blk, blk, qja, e_i, e_a, res) in enumerate(sectors):
+        oo, vv_ = e_i.numel(), e_a.numel()
+        g = torch.Generator(device=dev); g.manual_seed(77 + k)
+        u = torch.randn(p, generator=g, device=dev, dtype=torch.float64)
+        y = torch.zeros((oo, n), device=dev, dtype=torch.float64)
+        for i0 in range(0, blk[1] - blk[0], 8):
+            y[blk[0] + i0: blk[0] + i0 + 8] = torch.einsum("x,ixq->iq", u, ixq_blk[i0:i0 + 8, :, :n])
+        if world > 1:
+            lib.comm_allreduce(y)
+        ld = qja.shape[2]
+        z = (y @ qja.reshape(n, oo * ld)).reshape(oo, oo, ld)[:, :, :vv_]          # z[i, j, a]
+        limit = sample_limit if k == 1 else 0
+        mask = None
+        if limit > 0:
+            sb = lib.shard_sub_block(oo, p, ixq_blk.shape[2], world)
+            cov, _ = lib.shard_cover(oo, world, sb, limit)
+            mask = torch.from_numpy(cov).to(dev).to(torch.float64)                   # [i, j] = 1 for the pairs formed (i > j)
+        c0 = c1 = x0 = x1 = 0.0
+        for i0 in range(0, oo, 64):
+            i1 = min(oo, i0 + 64)
+            zi = z[i0:i1]                                   # [i, j, a]
+            zt = z[:, i0:i1].transpose(0, 1)                # [i, j, a] = z[j, i, a]
+            e = e_i[i0:i1, None, None] + e_i[None, :, None] - e_a[None, None, :]
+            sq = zi * zi
+            c0 += float(sq.sum()); c1 += float((sq * e).sum())
+            if mask is None:
+                ex = zi * zt
+            else:
+                d = zi - zt
+                ex = d * d * mask[i0:i1, :, None]
+            x0 += float(ex.sum()); x1 += float((ex * e).sum())
+        if mask is None:
+            want = ((os_f + ss_f) * c0 - ss_f * x0, (os_f + ss_f) * c1 - ss_f * x1)
+        else:
+            want = (os_f * c0 + ss_f * x0, os_f * c1 + ss_f * x1)
+        got = (float(u @ res[0] @ u), float(u @ res[1] @ u))
+        diffs.append(max(abs(got[m] - want[m]) / abs(want[m]) for m in range(2)))
+        del z, y
+    return {"max_rel_diff": max(diffs), "occupied_sector": diffs[0], "virtual_sector": diffs[1],
+            "note": "projection identity u^T vv u, u^T vev u of the %d-rank pole-sharded result against an independent "
+                    "evaluation from the projected (ix|Q) (torch.matmul), random u, both sectors at full size%s; the exact "
+                    "element-wise parity of the same code path against the reference is tests/test_multi_gpu.py"
+                    % (world, " (virtual sector: the sampled pairs)" if sample_limit > 0 else "")}
+
+
 def measure_fp64_peak(torch, dev, lib, seconds=1.5):
     """cuBLAS DGEMM 8192^3 (torch.matmul, f64) back to back for ~`seconds`, and the library's own GEMM on the same
     operands: the roofline denominator, measured beside the result."""
@@ -270,6 +323,12 @@ def main():
     ap.add_argument("--shape", default="100,1000,4000,1100")
     ap.add_argument("--os-factor", type=float, default=1.0)
     ap.add_argument("--ss-factor", type=float, default=1.0)
+    ap.add_argument("--sharded", action="store_true",
+                    help="pole-sharded build: every rank holds 1/N of (ix|Q), the other blocks visit over NVLink "
+                         "(for shapes whose (ix|Q) does not fit one GPU, e.g. --shape 250,2500,10000,2750)")
+    ap.add_argument("--sample-limit", type=int, default=0,
+                    help="--sharded only: run only the first m visiting sub-blocks of every ring step of the virtual-sector "
+                         "call (a bounded sample of a build that takes minutes) and extrapolate by the pair count")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=6.0, help="seconds per CPU sample (timed steps)")
@@ -322,9 +381,27 @@ def main():
         return torch.randn(sh, generator=g, device=dev, dtype=torch.float64) * scale
 
     sc = 1.0 / np.sqrt(n)
+    sharded = args.sharded
+    blk_o = lib.pole_block(o, rank, world) if sharded else (0, o)
+    blk_v = lib.pole_block(v, rank, world) if sharded else (0, v)
+
+    def make_poles(lo, hi, seed):
+        # (ix|Q) pole by pole, every pole from its own seed: any rank can regenerate any pole
+        ld = n + (n & 1)
+        t = torch.empty((hi - lo, p, ld), device=dev, dtype=torch.float64)
+        g = torch.Generator(device=dev)
+        for i in range(lo, hi):
+            g.manual_seed(seed * 1000003 + i)
+            torch.randn((p, ld), generator=g, device=dev, dtype=torch.float64, out=t[i - lo])
+        return t.mul_(sc)
+
     # occupied-sector call: o "occupied" poles, v "virtual"; virtual-sector call: roles swapped
-    ixq_o = make((o, p, n), sc, 1); qja_o = make((n, o, v), sc, 2)
-    ixq_v = make((v, p, n), sc, 3); qja_v = make((n, v, o), sc, 4)
+    if sharded:
+        ixq_o = make_poles(blk_o[0], blk_o[1], 1); ixq_v = make_poles(blk_v[0], blk_v[1], 3)
+    else:
+        ixq_o = make((o, p, n), sc, 1); ixq_v = make((v, p, n), sc, 3)
+    qja_o = make((n, o, v), sc, 2)
+    qja_v = make((n, v, o), sc, 4)
     ge = torch.Generator(device=dev); ge.manual_seed(5)       # (seeded: every rank must hold the same energies)
     e_o = torch.sort(torch.rand(o, generator=ge, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
     e_v = torch.sort(torch.rand(v, generator=ge, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
@@ -332,10 +409,19 @@ def main():
     out = torch.zeros((2, 2, p, p), device=dev, dtype=torch.float64)   # [sector][vv|vev]
     kw = dict(os_factor=os_f, ss_factor=ss_f, naux=n)
 
+    ev_mid = torch.cuda.Event(enable_timing=True)
+
     def step():
         # device-resident build: this rank's share of the pair-work items of both sectors; the all-reduce of the packed
         # [vv|vev] runs inside the library on the same stream (comm=True)
         out.zero_()
+        if sharded:
+            lib.set_option("shard_step_limit", 0)
+            lib.moments_rhf_dev_sharded(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=False, ei_host=eo_h, **kw)
+            ev_mid.record()
+            lib.set_option("shard_step_limit", args.sample_limit)
+            lib.moments_rhf_dev_sharded(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=False, ei_host=ev_h, **kw)
+            return
         lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=False, comm=True, ei_host=eo_h, **kw)
         lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=False, comm=True, ei_host=ev_h, **kw)
 
@@ -346,6 +432,19 @@ def main():
         events inside the library, so that every launch is timed alone on the GPU (with the overlap on two kernels
         share the SMs and their elapsed times add up to more than the wall time)."""
         out.zero_()
+        if sharded:
+            # one visiting sub-block per ring step of both sectors (the whole exchange pattern, a fraction of the pairs)
+            lib.set_option("shard_step_limit", 1)
+            if staged:
+                lib.set_overlap(False)
+            lib.moments_rhf_dev_sharded(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=staged, ei_host=eo_h, **kw)
+            s1, p1 = (lib.last_stage_ms(), lib.last_plan()) if staged else (None, None)
+            lib.moments_rhf_dev_sharded(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=staged, ei_host=ev_h, **kw)
+            s2, p2 = (lib.last_stage_ms(), lib.last_plan()) if staged else (None, None)
+            if staged:
+                lib.set_overlap(True)
+            lib.set_option("shard_step_limit", 0)
+            return s1, p1, s2, p2
         part = (w % WARM_PARTS) * world + rank
         if staged:
             lib.set_overlap(False)
@@ -386,6 +485,38 @@ def main():
     comm_bytes_step = lib.last_comm_bytes()[1] * 2 if world > 1 else 0      # two sectors
     checksum = float(out.sum().item())
     out_host = out.cpu().numpy().copy()
+    sharded_info = None
+    if sharded:
+        sb_o = lib.shard_sub_block(o, p, ixq_o.shape[2], world)
+        sb_v = lib.shard_sub_block(v, p, ixq_v.shape[2], world)
+        pole_bytes = p * ixq_o.shape[2] * 8
+        p2p_vir_measured = lib.last_p2p_bytes()          # last call of the last step = the virtual-sector call
+        sharded_info = {
+            "what": "pole-sharded build: rank r holds poles [nocc r/N, nocc (r+1)/N) of (ix|Q) only, (Q|ja) replicated; the "
+                    "other blocks visit in sub-blocks over NVLink (ncclSend/ncclRecv on a copy stream, double-buffered)",
+            "ixq_bytes_per_rank": {"occupied_sector": (blk_o[1] - blk_o[0]) * pole_bytes, "virtual_sector": (blk_v[1] - blk_v[0]) * pole_bytes},
+            "qja_bytes_per_rank": int(qja_o.numel() + qja_v.numel()) * 8,
+            "sub_block_poles": {"occupied_sector": sb_o, "virtual_sector": sb_v},
+            "nvlink_p2p_bytes_sent_per_rank_per_build": (world - 1) * ((blk_o[1] - blk_o[0]) + (blk_v[1] - blk_v[0])) * pole_bytes,
+            "nvlink_p2p_bytes_sent_virtual_sector_measured": p2p_vir_measured,
+        }
+    sampled = None
+    if sharded and args.sample_limit > 0:
+        # the virtual-sector call ran a sample of its pair-work items: extrapolate its pair-loop time by the pair count;
+        # the Coulomb stage (M build, T, moments: measured in the staged warm-up, not sampled) is added once
+        ms_occ = max_over_ranks(ev0.elapsed_time(ev_mid)) if args.steps == 1 else None
+        cov_s, st_s = lib.shard_cover(v, world, sb_v, args.sample_limit)
+        pairs_sampled, pairs_full = int(st_s[:, 0].max()), (v * (v - 1) // 2 + world - 1) // world
+        ms_vir = ms_per_step - (ms_occ if ms_occ is not None else 0.0)
+        coul_ms = staged[2][2] + staged[2][3]
+        ms_vir_full = coul_ms + max(ms_vir - coul_ms, 0.0) * pairs_full / max(pairs_sampled, 1)
+        sampled = {"what": "virtual-sector call: only the first %d visiting sub-block(s) of every ring step were run; value = "
+                           "occupied sector (complete) + Coulomb stage + pair-loop time x pairs_full / pairs_sampled"
+                           % args.sample_limit,
+                   "measured_ms_per_step": ms_per_step, "occupied_sector_ms": ms_occ, "virtual_sector_sampled_ms": ms_vir,
+                   "virtual_sector_coulomb_stage_ms": coul_ms, "pairs_sampled_per_rank": pairs_sampled,
+                   "pairs_full_per_rank": pairs_full, "virtual_sector_extrapolated_ms": ms_vir_full}
+        ms_per_step = (ms_occ if ms_occ is not None else 0.0) + ms_vir_full
 
     st1, pl1, st2, pl2 = staged
     k1_ms, k2_ms, m_ms, c_ms = [a + b for a, b in zip(st1, st2)]
@@ -398,6 +529,10 @@ def main():
     # ------------------------------------------------------------------ e2e (host buffers, every rank)
     e2e = None
     hosts = None
+    if sharded:       # no rank (and no host) holds the whole (ix|Q): the host-pointer ABI and the CPU loop do not apply
+        args.no_e2e = args.no_cpu = True
+        e2e = {"value": None, "unit": "s", "skipped": "pole-sharded build: the inputs exist only as per-GPU blocks in HBM (the "
+                                                      "whole (ix|Q) fits neither one GPU nor the host-pointer drop-in call)"}
     need_hosts = (not args.no_e2e) or (not args.no_cpu)
     if need_hosts:
         host_gb = ((o + v) * p * n + 2 * n * o * v) * 8 / 1e9
@@ -482,6 +617,10 @@ def main():
                                 % (secs[0], secs[1], lay[0], lay[1]),
                       "tflops_executed": 2.0 * f_alg(o, v, n, p) / o / per_pole * 1e-12,
                       "parity_max_rel_diff": parity["max_rel_diff"], "parity_note": parity["note"]}
+    if sharded:
+        parity = projection_parity(torch, lib, dev, world, rank, args.sample_limit,
+                                   ((ixq_o, blk_o, qja_o, e_o, e_v, out[0]), (ixq_v, blk_v, qja_v, e_v, e_o, out[1])),
+                                   n, p, os_f, ss_f)
     t_cpu = time.perf_counter() - t_cpu0
 
     if rank != 0:
@@ -535,6 +674,12 @@ def main():
         "wall_s": {"setup": t_setup, "warmup": t_warm, "timed": ms * 1e-3, "e2e_leg": t_e2e, "cpu_leg": t_cpu,
                    "total": time.perf_counter() - t_start},
     }
+    if sharded_info is not None:
+        line["sharded"] = sharded_info
+        line["config"]["parallelism"] = "pole-sharded (ix|Q): pole blocks visit over NVLink, pairs of a block pair split by " \
+                                        "parity, one all-gather of M0/M1 and one all-reduce of [vv|vev] per sector"
+    if sampled is not None:
+        line["sampled"] = sampled
     if e2e is not None:
         line["e2e"] = e2e
     if parity is not None:

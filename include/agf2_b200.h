@@ -104,7 +104,7 @@ int agf2_b200_ctx_get_device(agf2_b200_ctx *ctx, int *device);
 int agf2_b200_ctx_synchronize(agf2_b200_ctx *ctx);
 
 /* Options by name: "workspace_bytes", "overlap", "deterministic", "coulomb_factorization" (0/1/2),
- * "simple_kernels", "thin_tiles", "lpt_order", "tune_chunk", "profile".  ctx == NULL: the process
+ * "simple_kernels", "thin_tiles", "lpt_order", "tune_chunk", "profile", "visiting_bytes", "shard_step_limit".  ctx == NULL: the process
  * defaults, which the default contexts of all devices share. */
 int agf2_b200_ctx_set_option(agf2_b200_ctx *ctx, const char *name, int64_t value);
 
@@ -150,6 +150,34 @@ int agf2_b200_ctx_moments_uhf_dev(agf2_b200_ctx *ctx, const double *ixq_a, int64
                                   int64_t nocc_a, int64_t nocc_b, int64_t nvir_a, int64_t nvir_b, int64_t naux,
                                   int64_t istart, int64_t iend, double os_factor, double ss_factor, double *vv,
                                   double *vev, void *stream, int sync);
+
+/* POLE-SHARDED build, for shapes whose (ix|Q) tensor does not fit one GPU (BASELINE configs[4]: nocc=250,
+ * nvir=2500, naux=10000, nphys=2750 -- the virtual-sector (ix|Q) is 550 GB).  Rank r of the context's communicator
+ * holds only the poles [lo, hi) = agf2_b200_pole_block(nocc, r, nranks) of (ix|Q) (`ixq_block`, (hi - lo, nphys,
+ * ld_ixq)); qja, ei, ea are complete on every rank.  Pairs inside a block are formed by its owner; for the pairs
+ * between two blocks the poles of one block VISIT the other GPU in sub-blocks ("visiting_bytes" option, default 1 GiB,
+ * two buffers) sent by ncclSend/ncclRecv over NVLink on a copy stream while the previous sub-block is being worked
+ * on; the two owners of a block pair split its pairs by the parity of i + j.  The Coulomb-type terms go through the
+ * M0/M1 factorisation (M rows built 1/N per rank and all-gathered, every rank treats its own poles), then the one
+ * all-reduce of [vv | vev].  Same result as the replicated build to rounding; replaces the replicated host arrays of
+ * auxgf/mpi/agf2/optragf2.py:370-374.  Whole pole range only (no [istart, iend) slice), RHF only. */
+int agf2_b200_pole_block(int64_t nocc, int64_t rank, int64_t nranks, int64_t *lo, int64_t *hi);
+int agf2_b200_ctx_moments_rhf_dev_sharded(agf2_b200_ctx *ctx, const double *ixq_block, int64_t ld_ixq,
+                                          const double *qja, int64_t ld_qja, const double *ei, const double *ea,
+                                          const double *ei_host, int64_t nphys, int64_t nocc, int64_t nvir,
+                                          int64_t naux, double os_factor, double ss_factor, double *vv,
+                                          double *vev, void *stream, int sync);
+/* Host-only replay of the pole-sharded schedule (no GPU): cover (nocc x nocc int64, accumulated into) counts how
+ * often the unordered pair {i, j} is formed by any of the `nranks` ranks at [max(i,j), min(i,j)] (must be exactly 1),
+ * stats (nranks x 2) = pairs formed / poles sent per rank, for sub-blocks of `sub_block` poles.  limit > 0: the
+ * sampled schedule of the "shard_step_limit" option (only the first `limit` sub-blocks of every ring step -- a
+ * bounded benchmark sample of a build that would take minutes; the result is then NOT the full moments). */
+int agf2_b200_shard_cover(int64_t nocc, int64_t nranks, int64_t sub_block, int64_t limit, int64_t *cover,
+                          int64_t *stats);
+/* poles per visiting sub-block a pole-sharded build of this shape uses on the context ("visiting_bytes" option) */
+int64_t agf2_b200_ctx_shard_sub_block(agf2_b200_ctx *ctx, int64_t nocc, int64_t nphys, int64_t ld_ixq, int64_t nranks);
+/* bytes this rank SENT point-to-point (visiting pole blocks) in the last call on the context */
+int64_t agf2_b200_ctx_last_p2p_bytes(agf2_b200_ctx *ctx);
 
 /* Host-pointer build on a context with a communicator -- the multi-GPU form of the drop-in call: every
  * rank passes the same host arrays; rank r copies 1/N of ixq (groups of poles, pipelined under the

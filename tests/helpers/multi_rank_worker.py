@@ -71,6 +71,32 @@ def main():
     assert np.array_equal(outs[0], outs[1]), "multi-rank build is not bit-reproducible"
     same_on_all_ranks(outs[0], "moments_rhf_dev(comm=True)")
 
+    # --- pole-sharded build: every rank holds only its block of (ix|Q); the other blocks visit over NVLink in
+    # sub-blocks (tiny sub-blocks here so that the double-buffered exchange is exercised), SCS factors, ragged sizes,
+    # bit-reproducible and identical on every rank
+    for (o, v, n, p, seed, os_f, ss_f, vis) in ((14, 50, 120, 70, 21, 1.0, 1.0, 1 << 30), (37, 21, 130, 141, 22, 1.2, 1.0 / 3.0, 3 * 141 * 130 * 8),
+                                                (50, 12, 96, 264, 23, 1.0, 1.0, 264 * 96 * 8), (9, 30, 64, 40, 24, 0.7, 0.0, 1 << 30)):
+        if o < world:
+            continue
+        ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, seed)
+        lo, hi = lib.pole_block(o, rank, world)
+        blk = T(ixq.reshape(o, p, n)[lo:hi], (hi - lo, p, n))
+        dq = (T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))
+        lib.set_option("visiting_bytes", vis)
+        outs = []
+        for _ in range(2):
+            out = torch.full((2, p, p), 0.25, dtype=torch.float64, device=dev)
+            lib.moments_rhf_dev_sharded(blk, *dq, os_factor=os_f, ss_factor=ss_f, vv=out[0], vev=out[1], sync=True, ei_host=ei)
+            outs.append(out.cpu().numpy() - 0.25)
+        r = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o, os_f, ss_f)
+        assert relerr(outs[0][0], r[0]) < TOL and relerr(outs[0][1], r[1]) < TOL, \
+            ("sharded", o, v, n, p, relerr(outs[0][0], r[0]), relerr(outs[0][1], r[1]))
+        assert np.array_equal(outs[0], outs[1]), "pole-sharded build is not bit-reproducible"
+        same_on_all_ranks(outs[0], "moments_rhf_dev_sharded")
+        if world > 1 and ss_f != 0.0:
+            assert lib.last_p2p_bytes() == (world - 1) * (hi - lo) * p * n * 8, lib.last_p2p_bytes()
+    lib.set_option("visiting_bytes", 1 << 30)
+
     # --- the driver: N ranks on the CUDA backend vs the oracle backend in-process
     from auxgf_b200 import backend
     from auxgf_b200.agf2 import OptRAGF2

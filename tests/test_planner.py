@@ -130,3 +130,17 @@ def test_coverage_property_random_shapes():
         assert all(s["max_cols"] <= s["cap_cols"] for s in stats)
 
     check()
+
+
+@pytest.mark.parametrize("nocc,nranks,sb", [(10, 2, 3), (17, 3, 2), (64, 8, 1), (250, 8, 9), (33, 4, 100), (8, 8, 5), (41, 5, 4)])
+def test_pole_sharded_schedule_covers_every_pair_once(nocc, nranks, sb):
+    """The pole-sharded schedule (own block, then visiting sub-blocks split by the parity of i + j) forms every
+    unordered pole pair exactly once over all ranks, balanced, and every rank sends its block to every other rank."""
+    cover, stats = lib.shard_cover(nocc, nranks, sb)
+    assert np.array_equal(cover, np.tril(np.ones((nocc, nocc), dtype=np.int64), -1))
+    assert stats[:, 0].sum() == nocc * (nocc - 1) // 2
+    for r in range(nranks):
+        lo, hi = lib.pole_block(nocc, r, nranks)
+        assert stats[r, 1] == (nranks - 1) * (hi - lo)
+    if nocc >= 8 * nranks:
+        assert stats[:, 0].max() <= 1.15 * stats[:, 0].min()
