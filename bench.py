@@ -245,7 +245,8 @@ def projection_parity(torch, lib, dev, world, rank, sample_limit, sectors, n, p,
         u = torch.randn(p, generator=g, device=dev, dtype=torch.float64)
         y = torch.zeros((oo, n), device=dev, dtype=torch.float64)
         for i0 in range(0, blk[1] - blk[0], 8):
-            y[blk[0] + i0: blk[0] + i0 + 8] = torch.einsum("x,ixq->iq", u, ixq_blk[i0:i0 + 8, :, :n])
+            i1 = min(blk[1] - blk[0], i0 + 8)
+            y[blk[0] + i0: blk[0] + i1] = torch.einsum("x,ixq->iq", u, ixq_blk[i0:i1, :, :n])
         if world > 1:
             lib.comm_allreduce(y)
         ld = qja.shape[2]

@@ -81,7 +81,9 @@ def main():
         ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, seed)
         lo, hi = lib.pole_block(o, rank, world)
         blk = T(ixq.reshape(o, p, n)[lo:hi], (hi - lo, p, n))
-        dq = (T(qja, (n, o, v)), T(ei, (o,)), T(ea, (v,)))
+        qpad = np.zeros((n, o, v + (v & 1)))                 # device arrays need an even pitch (16-byte TMA strides)
+        qpad[:, :, :v] = qja.reshape(n, o, v)
+        dq = (T(qpad, qpad.shape), T(ei, (o,)), T(ea, (v,)))
         lib.set_option("visiting_bytes", vis)
         outs = []
         for _ in range(2):
@@ -123,4 +125,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:      # the launcher's banner buries the traceback: say what failed on stdout too
+        import traceback
+        print("RANK %s FAILED: %r\n%s" % (os.environ.get("RANK", "?"), exc, traceback.format_exc()), flush=True)
+        raise

@@ -28,4 +28,11 @@ def test_multi_rank_nccl_parity(world):
            os.path.join(ROOT, "tests", "helpers", "multi_rank_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     ok = len(set(re.findall(r"RANK (\d+) OK", out.stdout)))     # (the ranks' lines may interleave)
+    if out.returncode != 0 or ok != world:
+        fails = re.findall(r"RANK \S+ FAILED: .*", out.stdout)
+        log = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(log):
+            with open(os.path.join(log, "multi_rank_fail_%d.log" % world), "w") as f:
+                f.write(out.stdout + "\n==== stderr ====\n" + out.stderr)
+        assert False, (fails[:2], out.stdout[-1500:], out.stderr[-1500:])
     assert out.returncode == 0 and ok == world, (out.stdout[-3000:], out.stderr[-3000:])
