@@ -8,6 +8,7 @@ auxgf/agf2/optragf2.py:283-293), F_alg = 1.50e15 flop.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
                     [--shape nocc,nvir,naux,nphys] [--os-factor f] [--ss-factor f] [--no-e2e] [--no-cpu]
+                    [--sharded [--sample-limit m]]
 
   value    : seconds per moment build with the DF tensors already resident in HBM (device C-ABI)
   e2e      : the same build through the reference-facing host-pointer C-ABI
@@ -231,58 +232,211 @@ def reference_arm(args, o, v, n, p):
     return 0
 
 
-def projection_parity(torch, lib, dev, world, rank, sample_limit, sectors, n, p, os_f, ss_f):
-    """Size-independent check of a (pole-sharded) build against an independent evaluation: for a random vector u,
+def projection_parity(torch, lib, dev, world, k, limit, ixq_blk, blk, qja, e_i, e_a, res, n, p, os_f, ss_f):
+    """Size-independent check of one pole-sharded sector call against an independent evaluation: for a random vector u,
         u^T vv u = (os+ss) sum_ija z_ija^2 - ss sum_ija z_ija z_jia ,   z_ija = sum_Q (u^T ixq_i)[Q] qja[Q, j, a]
     (and the same with the weights e_i + e_j - e_a for vev) costs 1/nphys of the build and needs no integral block: the
     projected (ix|Q) of every rank's poles is all-reduced, z comes from one library-independent torch.matmul (cuBLAS).
-    With a sampled virtual-sector call the exchange-type sum runs over exactly the pairs the sample formed (replayed on
-    the host by agf2_b200_shard_cover)."""
-    diffs = []
-    for k, (ixq_blk, blk, qja, e_i, e_a, res) in enumerate(sectors):
-        oo, vv_ = e_i.numel(), e_a.numel()
-        g = torch.Generator(device=dev); g.manual_seed(77 + k)
-        u = torch.randn(p, generator=g, device=dev, dtype=torch.float64)
-        y = torch.zeros((oo, n), device=dev, dtype=torch.float64)
-        for i0 in range(0, blk[1] - blk[0], 8):
-            i1 = min(blk[1] - blk[0], i0 + 8)
-            y[blk[0] + i0: blk[0] + i1] = torch.einsum("x,ixq->iq", u, ixq_blk[i0:i1, :, :n])
-        if world > 1:
-            lib.comm_allreduce(y)
-        ld = qja.shape[2]
-        z = (y @ qja.reshape(n, oo * ld)).reshape(oo, oo, ld)[:, :, :vv_]          # z[i, j, a]
-        limit = sample_limit if k == 1 else 0
-        mask = None
-        if limit > 0:
-            sb = lib.shard_sub_block(oo, p, ixq_blk.shape[2], world)
-            cov, _ = lib.shard_cover(oo, world, sb, limit)
-            mask = torch.from_numpy(cov).to(dev).to(torch.float64)                   # [i, j] = 1 for the pairs formed (i > j)
-        c0 = c1 = x0 = x1 = 0.0
-        for i0 in range(0, oo, 64):
-            i1 = min(oo, i0 + 64)
-            zi = z[i0:i1]                                   # [i, j, a]
-            zt = z[:, i0:i1].transpose(0, 1)                # [i, j, a] = z[j, i, a]
-            e = e_i[i0:i1, None, None] + e_i[None, :, None] - e_a[None, None, :]
-            sq = zi * zi
-            c0 += float(sq.sum()); c1 += float((sq * e).sum())
-            if mask is None:
-                ex = zi * zt
-            else:
-                d = zi - zt
-                ex = d * d * mask[i0:i1, :, None]
-            x0 += float(ex.sum()); x1 += float((ex * e).sum())
+    With a sampled call (limit > 0) the exchange-type sum runs over exactly the pairs the sample formed (replayed on the
+    host by agf2_b200_shard_cover)."""
+    oo, vv_ = e_i.numel(), e_a.numel()
+    g = torch.Generator(device=dev); g.manual_seed(77 + k)
+    u = torch.randn(p, generator=g, device=dev, dtype=torch.float64)
+    y = torch.zeros((oo, n), device=dev, dtype=torch.float64)
+    for i0 in range(0, blk[1] - blk[0], 8):
+        i1 = min(blk[1] - blk[0], i0 + 8)
+        y[blk[0] + i0: blk[0] + i1] = torch.einsum("x,ixq->iq", u, ixq_blk[i0:i1, :, :n])
+    if world > 1:
+        lib.comm_allreduce(y)
+    ld = qja.shape[2]
+    z = (y @ qja.reshape(n, oo * ld)).reshape(oo, oo, ld)[:, :, :vv_]          # z[i, j, a]
+    mask = None
+    if limit > 0:
+        sb = lib.shard_sub_block(oo, p, ixq_blk.shape[2], world)
+        cov, _ = lib.shard_cover(oo, world, sb, limit)
+        mask = torch.from_numpy(cov).to(dev).to(torch.float64)                   # [i, j] = 1 for the pairs formed (i > j)
+    c0 = c1 = x0 = x1 = 0.0
+    for i0 in range(0, oo, 32):
+        i1 = min(oo, i0 + 32)
+        zi = z[i0:i1]                                   # [i, j, a]
+        zt = z[:, i0:i1].transpose(0, 1)                # [i, j, a] = z[j, i, a]
+        e = e_i[i0:i1, None, None] + e_i[None, :, None] - e_a[None, None, :]
+        sq = zi * zi
+        c0 += float(sq.sum()); c1 += float((sq * e).sum())
         if mask is None:
-            want = ((os_f + ss_f) * c0 - ss_f * x0, (os_f + ss_f) * c1 - ss_f * x1)
+            ex = zi * zt
         else:
-            want = (os_f * c0 + ss_f * x0, os_f * c1 + ss_f * x1)
-        got = (float(u @ res[0] @ u), float(u @ res[1] @ u))
-        diffs.append(max(abs(got[m] - want[m]) / abs(want[m]) for m in range(2)))
-        del z, y
-    return {"max_rel_diff": max(diffs), "occupied_sector": diffs[0], "virtual_sector": diffs[1],
-            "note": "projection identity u^T vv u, u^T vev u of the %d-rank pole-sharded result against an independent "
-                    "evaluation from the projected (ix|Q) (torch.matmul), random u, both sectors at full size%s; the exact "
-                    "element-wise parity of the same code path against the reference is tests/test_multi_gpu.py"
-                    % (world, " (virtual sector: the sampled pairs)" if sample_limit > 0 else "")}
+            d = zi - zt
+            ex = d * d * mask[i0:i1, :, None]
+        x0 += float(ex.sum()); x1 += float((ex * e).sum())
+    if mask is None:
+        want = ((os_f + ss_f) * c0 - ss_f * x0, (os_f + ss_f) * c1 - ss_f * x1)
+    else:
+        want = (os_f * c0 + ss_f * x0, os_f * c1 + ss_f * x1)
+    got = (float(u @ res[0] @ u), float(u @ res[1] @ u))
+    rel = [abs(got[m] - want[m]) / abs(want[m]) for m in range(2)]
+    return {"max_rel_diff": max(rel), "vv": rel[0], "vev": rel[1]}
+
+
+def sharded_arm(args, o, v, n, p, torch, lib, mpi, dev, rank, world, local_rank, t_start):
+    """--sharded: the pole-sharded build (agf2_b200_ctx_moments_rhf_dev_sharded).  The two sector calls are generated,
+    warmed up, timed and checked one after the other (at the L shape one sector's blocks fill a GPU: 69 GB of (ix|Q) +
+    50 GB of (Q|ja) per rank for the virtual sector); a step = occupied-sector call + virtual-sector call, each timed with
+    its inputs resident in HBM."""
+    os_f, ss_f = args.os_factor, args.ss_factor
+    flops_build = f_alg(o, v, n, p) + f_alg(v, o, n, p)
+
+    if args.sharded:
+        return sharded_arm(args, o, v, n, p, torch, lib, mpi, dev, rank, world, local_rank, t_start)
+
+    def sync_all():
+        if world > 1:
+            lib.comm_barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            lib.comm_allreduce(t, "max")
+        return float(t.item())
+
+    sampler_peak = ClockSampler(local_rank).start() if rank == 0 else None
+    peaks = measure_fp64_peak(torch, dev, lib)
+    peak_clocks = sampler_peak.stop() if rank == 0 else None
+    peak = peaks["cublas"]
+    sc = 1.0 / np.sqrt(n)
+    ge = torch.Generator(device=dev); ge.manual_seed(5)
+    e_o = torch.sort(torch.rand(o, generator=ge, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
+    e_v = torch.sort(torch.rand(v, generator=ge, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
+    eo_h, ev_h = e_o.cpu().numpy(), e_v.cpu().numpy()
+    kw = dict(os_factor=os_f, ss_factor=ss_f, naux=n)
+    t_setup = time.perf_counter() - t_start
+
+    sectors = []
+    clocks_all = []
+    launches = 0
+    executed = [0.0, 0.0, 0.0]
+    checksum = 0.0
+    for k, (oo, vv_, ei, ea, eh, seed, limit) in enumerate(((o, v, e_o, e_v, eo_h, 1, 0), (v, o, e_v, e_o, ev_h, 3, args.sample_limit))):
+        lo, hi = lib.pole_block(oo, rank, world)
+        ld = n + (n & 1)
+        ixq = torch.empty((hi - lo, p, ld), device=dev, dtype=torch.float64)
+        g = torch.Generator(device=dev)
+        for i in range(lo, hi):                       # every pole from its own seed: any rank could regenerate any pole
+            g.manual_seed(seed * 1000003 + i)
+            torch.randn((p, ld), generator=g, device=dev, dtype=torch.float64, out=ixq[i - lo])
+        ixq.mul_(sc)
+        ldv = vv_ + (vv_ & 1)
+        g.manual_seed(seed + 1)                       # (Q|ja): the same on every rank
+        qja = torch.empty((n, oo, ldv), device=dev, dtype=torch.float64)
+        for q0 in range(0, n, 256):
+            torch.randn((min(n, q0 + 256) - q0, oo, ldv), generator=g, device=dev, dtype=torch.float64, out=qja[q0:q0 + 256])
+        qja.mul_(sc)
+        res = torch.zeros((2, p, p), device=dev, dtype=torch.float64)
+        sb = lib.shard_sub_block(oo, p, ld, world)
+
+        def call(sync):
+            res.zero_()
+            lib.moments_rhf_dev_sharded(ixq, qja, ei, ea, vv=res[0], vev=res[1], sync=sync, ei_host=eh, **kw)
+
+        # warm-up: one visiting sub-block per ring step (the whole exchange pattern, a fraction of the pairs); the last one
+        # with the two-stream overlap off and per-launch CUDA events (stage times)
+        lib.set_option("shard_step_limit", 1)
+        stage = plan = None
+        for w in range(max(args.warmup, 1)):
+            last = w == max(args.warmup, 1) - 1
+            if last:
+                lib.set_overlap(False)
+            call(last)
+            if last:
+                stage, plan = lib.last_stage_ms(), lib.last_plan()
+                lib.set_overlap(True)
+        lib.set_option("shard_step_limit", limit)
+        sync_all()
+        lib.launch_count(reset=True)
+        lib.flop_counters(reset=True)
+        sampler = ClockSampler(local_rank).start() if rank == 0 else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            call(False)
+        ev1.record()
+        sync_all()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+        if rank == 0:
+            clocks_all.append(sampler.stop())
+        launches += lib.launch_count()
+        executed = [a + b / args.steps for a, b in zip(executed, lib.flop_counters())]
+        p2p = lib.last_p2p_bytes()
+        gathered, reduced = lib.last_comm_bytes()
+        checksum += float(res.sum().item())
+        par = projection_parity(torch, lib, dev, world, k, limit, ixq, (lo, hi), qja, ei, ea, res, n, p, os_f, ss_f)
+        pairs_full = (oo * (oo - 1) // 2 + world - 1) // world
+        pairs_run = pairs_full
+        ms_full = ms
+        coul_ms = stage[2] + stage[3]
+        if limit > 0:
+            pairs_run = int(lib.shard_cover(oo, world, sb, limit)[1][:, 0].max())
+            ms_full = coul_ms + max(ms - coul_ms, 0.0) * pairs_full / max(pairs_run, 1)
+        pole_bytes = p * ld * 8
+        sectors.append({"nocc": oo, "nvir": vv_, "ms_measured": ms, "ms": ms_full, "sampled_sub_blocks_per_ring_step": limit,
+                        "pairs_run_per_rank": pairs_run, "pairs_full_per_rank": pairs_full, "coulomb_stage_ms": coul_ms,
+                        "sub_block_poles": sb, "ixq_bytes_per_rank": (hi - lo) * pole_bytes, "qja_bytes_per_rank": qja.numel() * 8,
+                        "nvlink_p2p_bytes_sent_per_rank_measured": p2p,
+                        "nvlink_p2p_bytes_sent_per_rank_full_build": (world - 1) * (hi - lo) * pole_bytes,
+                        "nvlink_allgather_bytes_sent_per_rank": gathered, "nvlink_allreduce_bytes_sent_per_rank": reduced,
+                        "projection_parity": par, "stage": stage, "plan": plan})
+        del ixq, qja, res
+        torch.cuda.empty_cache()
+
+    ms_per_step = sectors[0]["ms"] + sectors[1]["ms"]
+    if rank != 0:
+        mpi.finalize()
+        return 0
+    k1_ms = sum(s["stage"][0] for s in sectors)
+    k1_flops = sum(2.0 * p * n * 2 * s["plan"]["pair"] * s["nvir"] for s in sectors)
+    k1_tf = k1_flops / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else None
+    sampled = any(s["sampled_sub_blocks_per_ring_step"] > 0 for s in sectors)
+    parity = {"max_rel_diff": max(s["projection_parity"]["max_rel_diff"] for s in sectors),
+              "occupied_sector": sectors[0]["projection_parity"]["max_rel_diff"],
+              "virtual_sector": sectors[1]["projection_parity"]["max_rel_diff"],
+              "note": "projection identity u^T vv u, u^T vev u (random u) of the %d-rank pole-sharded result against an "
+                      "independent evaluation from the projected (ix|Q) (one torch.matmul per sector), at full size%s; the "
+                      "element-wise parity of this code path against the reference is tests/test_multi_gpu.py"
+                      % (world, "; virtual sector: over exactly the sampled pairs" if sampled else "")}
+    cfg = make_config(o, v, n, p, os_f, ss_f)
+    cfg["parallelism"] = "pole-sharded (ix|Q): pole blocks visit over NVLink (ncclSend/ncclRecv, double-buffered under the " \
+                         "pair loop), the pairs of a block pair split by parity, M0/M1 all-gathered, one all-reduce of [vv|vev] per sector"
+    for s in sectors:
+        s.pop("projection_parity"); s["stage_ms"] = dict(zip(("k1_form", "k2_moment", "m_build", "coulomb"), s.pop("stage")))
+    line = {
+        "metric": "agf2_moment_build_seconds_per_iter", "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "tflops": flops_build / (ms_per_step * 1e-3) * 1e-12,
+        "algorithmic_tflops_over_peak": flops_build / (ms_per_step * 1e-3) * 1e-12 / (peak * world),
+        "extrapolated": ("value = occupied sector (complete) + virtual sector extrapolated from a sample of its pair-work items "
+                         "(first %d visiting sub-block(s) of every ring step): Coulomb stage + pair-loop time x pairs_full / "
+                         "pairs_run; see `sectors`" % args.sample_limit) if sampled else None,
+        "fp64_peak_tflops": peak, "fp64_peak_source": "cublasDgemm 8192^3 (torch.matmul f64) timed for 1.5 s in this run",
+        "fp64_peak_clocks": peak_clocks, "inhouse_gemm_tflops": peaks["inhouse"],
+        "roofline": {"bound": "tensor", "kernel": "k1_form (FP64 DMMA.8x8x4)", "achieved": k1_tf, "peak": peak,
+                     "unit": "TFLOP/s", "frac": (k1_tf / peak) if k1_tf else None, "traffic": None,
+                     "flop_per_block": "2 * nphys * nvir * naux (one (xi|ja) block of one pole pair)",
+                     "staged_slice": "one visiting sub-block per ring step of both sectors, overlap off, CUDA events around "
+                                     "every launch (last warm-up step of each sector)"},
+        "gpu_launches": int(launches), "clocks": clocks_all[-1] if clocks_all else None, "clocks_occupied_sector": clocks_all[0] if clocks_all else None,
+        "checksum": checksum, "sectors": sectors, "parity": parity,
+        "nvlink_bytes_sent_per_rank_per_build": sum(s["nvlink_p2p_bytes_sent_per_rank_full_build"] + s["nvlink_allgather_bytes_sent_per_rank"]
+                                                    + s["nvlink_allreduce_bytes_sent_per_rank"] for s in sectors),
+        "e2e": {"value": None, "unit": "s", "skipped": "pole-sharded build: the inputs exist only as per-GPU blocks in HBM (the whole "
+                                                       "(ix|Q) fits neither one GPU nor the host-pointer drop-in call)"},
+        "wall_s": {"setup": t_setup, "total": time.perf_counter() - t_start},
+    }
+    print(json.dumps(line))
+    mpi.finalize()
+    return 0
 
 
 def measure_fp64_peak(torch, dev, lib, seconds=1.5):
@@ -382,27 +536,9 @@ def main():
         return torch.randn(sh, generator=g, device=dev, dtype=torch.float64) * scale
 
     sc = 1.0 / np.sqrt(n)
-    sharded = args.sharded
-    blk_o = lib.pole_block(o, rank, world) if sharded else (0, o)
-    blk_v = lib.pole_block(v, rank, world) if sharded else (0, v)
-
-    def make_poles(lo, hi, seed):
-        # (ix|Q) pole by pole, every pole from its own seed: any rank can regenerate any pole
-        ld = n + (n & 1)
-        t = torch.empty((hi - lo, p, ld), device=dev, dtype=torch.float64)
-        g = torch.Generator(device=dev)
-        for i in range(lo, hi):
-            g.manual_seed(seed * 1000003 + i)
-            torch.randn((p, ld), generator=g, device=dev, dtype=torch.float64, out=t[i - lo])
-        return t.mul_(sc)
-
     # occupied-sector call: o "occupied" poles, v "virtual"; virtual-sector call: roles swapped
-    if sharded:
-        ixq_o = make_poles(blk_o[0], blk_o[1], 1); ixq_v = make_poles(blk_v[0], blk_v[1], 3)
-    else:
-        ixq_o = make((o, p, n), sc, 1); ixq_v = make((v, p, n), sc, 3)
-    qja_o = make((n, o, v), sc, 2)
-    qja_v = make((n, v, o), sc, 4)
+    ixq_o = make((o, p, n), sc, 1); qja_o = make((n, o, v), sc, 2)
+    ixq_v = make((v, p, n), sc, 3); qja_v = make((n, v, o), sc, 4)
     ge = torch.Generator(device=dev); ge.manual_seed(5)       # (seeded: every rank must hold the same energies)
     e_o = torch.sort(torch.rand(o, generator=ge, device=dev, dtype=torch.float64) * 1.5 - 2.0)[0]
     e_v = torch.sort(torch.rand(v, generator=ge, device=dev, dtype=torch.float64) * 2.5 + 0.5)[0]
@@ -410,19 +546,10 @@ def main():
     out = torch.zeros((2, 2, p, p), device=dev, dtype=torch.float64)   # [sector][vv|vev]
     kw = dict(os_factor=os_f, ss_factor=ss_f, naux=n)
 
-    ev_mid = torch.cuda.Event(enable_timing=True)
-
     def step():
         # device-resident build: this rank's share of the pair-work items of both sectors; the all-reduce of the packed
         # [vv|vev] runs inside the library on the same stream (comm=True)
         out.zero_()
-        if sharded:
-            lib.set_option("shard_step_limit", 0)
-            lib.moments_rhf_dev_sharded(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=False, ei_host=eo_h, **kw)
-            ev_mid.record()
-            lib.set_option("shard_step_limit", args.sample_limit)
-            lib.moments_rhf_dev_sharded(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=False, ei_host=ev_h, **kw)
-            return
         lib.moments_rhf_dev(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=False, comm=True, ei_host=eo_h, **kw)
         lib.moments_rhf_dev(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=False, comm=True, ei_host=ev_h, **kw)
 
@@ -433,19 +560,6 @@ def main():
         events inside the library, so that every launch is timed alone on the GPU (with the overlap on two kernels
         share the SMs and their elapsed times add up to more than the wall time)."""
         out.zero_()
-        if sharded:
-            # one visiting sub-block per ring step of both sectors (the whole exchange pattern, a fraction of the pairs)
-            lib.set_option("shard_step_limit", 1)
-            if staged:
-                lib.set_overlap(False)
-            lib.moments_rhf_dev_sharded(ixq_o, qja_o, e_o, e_v, vv=out[0, 0], vev=out[0, 1], sync=staged, ei_host=eo_h, **kw)
-            s1, p1 = (lib.last_stage_ms(), lib.last_plan()) if staged else (None, None)
-            lib.moments_rhf_dev_sharded(ixq_v, qja_v, e_v, e_o, vv=out[1, 0], vev=out[1, 1], sync=staged, ei_host=ev_h, **kw)
-            s2, p2 = (lib.last_stage_ms(), lib.last_plan()) if staged else (None, None)
-            if staged:
-                lib.set_overlap(True)
-            lib.set_option("shard_step_limit", 0)
-            return s1, p1, s2, p2
         part = (w % WARM_PARTS) * world + rank
         if staged:
             lib.set_overlap(False)
@@ -486,38 +600,6 @@ def main():
     comm_bytes_step = lib.last_comm_bytes()[1] * 2 if world > 1 else 0      # two sectors
     checksum = float(out.sum().item())
     out_host = out.cpu().numpy().copy()
-    sharded_info = None
-    if sharded:
-        sb_o = lib.shard_sub_block(o, p, ixq_o.shape[2], world)
-        sb_v = lib.shard_sub_block(v, p, ixq_v.shape[2], world)
-        pole_bytes = p * ixq_o.shape[2] * 8
-        p2p_vir_measured = lib.last_p2p_bytes()          # last call of the last step = the virtual-sector call
-        sharded_info = {
-            "what": "pole-sharded build: rank r holds poles [nocc r/N, nocc (r+1)/N) of (ix|Q) only, (Q|ja) replicated; the "
-                    "other blocks visit in sub-blocks over NVLink (ncclSend/ncclRecv on a copy stream, double-buffered)",
-            "ixq_bytes_per_rank": {"occupied_sector": (blk_o[1] - blk_o[0]) * pole_bytes, "virtual_sector": (blk_v[1] - blk_v[0]) * pole_bytes},
-            "qja_bytes_per_rank": int(qja_o.numel() + qja_v.numel()) * 8,
-            "sub_block_poles": {"occupied_sector": sb_o, "virtual_sector": sb_v},
-            "nvlink_p2p_bytes_sent_per_rank_per_build": (world - 1) * ((blk_o[1] - blk_o[0]) + (blk_v[1] - blk_v[0])) * pole_bytes,
-            "nvlink_p2p_bytes_sent_virtual_sector_measured": p2p_vir_measured,
-        }
-    sampled = None
-    if sharded and args.sample_limit > 0:
-        # the virtual-sector call ran a sample of its pair-work items: extrapolate its pair-loop time by the pair count;
-        # the Coulomb stage (M build, T, moments: measured in the staged warm-up, not sampled) is added once
-        ms_occ = max_over_ranks(ev0.elapsed_time(ev_mid)) if args.steps == 1 else None
-        cov_s, st_s = lib.shard_cover(v, world, sb_v, args.sample_limit)
-        pairs_sampled, pairs_full = int(st_s[:, 0].max()), (v * (v - 1) // 2 + world - 1) // world
-        ms_vir = ms_per_step - (ms_occ if ms_occ is not None else 0.0)
-        coul_ms = staged[2][2] + staged[2][3]
-        ms_vir_full = coul_ms + max(ms_vir - coul_ms, 0.0) * pairs_full / max(pairs_sampled, 1)
-        sampled = {"what": "virtual-sector call: only the first %d visiting sub-block(s) of every ring step were run; value = "
-                           "occupied sector (complete) + Coulomb stage + pair-loop time x pairs_full / pairs_sampled"
-                           % args.sample_limit,
-                   "measured_ms_per_step": ms_per_step, "occupied_sector_ms": ms_occ, "virtual_sector_sampled_ms": ms_vir,
-                   "virtual_sector_coulomb_stage_ms": coul_ms, "pairs_sampled_per_rank": pairs_sampled,
-                   "pairs_full_per_rank": pairs_full, "virtual_sector_extrapolated_ms": ms_vir_full}
-        ms_per_step = (ms_occ if ms_occ is not None else 0.0) + ms_vir_full
 
     st1, pl1, st2, pl2 = staged
     k1_ms, k2_ms, m_ms, c_ms = [a + b for a, b in zip(st1, st2)]
@@ -530,10 +612,6 @@ def main():
     # ------------------------------------------------------------------ e2e (host buffers, every rank)
     e2e = None
     hosts = None
-    if sharded:       # no rank (and no host) holds the whole (ix|Q): the host-pointer ABI and the CPU loop do not apply
-        args.no_e2e = args.no_cpu = True
-        e2e = {"value": None, "unit": "s", "skipped": "pole-sharded build: the inputs exist only as per-GPU blocks in HBM (the "
-                                                      "whole (ix|Q) fits neither one GPU nor the host-pointer drop-in call)"}
     need_hosts = (not args.no_e2e) or (not args.no_cpu)
     if need_hosts:
         host_gb = ((o + v) * p * n + 2 * n * o * v) * 8 / 1e9
@@ -618,10 +696,6 @@ def main():
                                 % (secs[0], secs[1], lay[0], lay[1]),
                       "tflops_executed": 2.0 * f_alg(o, v, n, p) / o / per_pole * 1e-12,
                       "parity_max_rel_diff": parity["max_rel_diff"], "parity_note": parity["note"]}
-    if sharded:
-        parity = projection_parity(torch, lib, dev, world, rank, args.sample_limit,
-                                   ((ixq_o, blk_o, qja_o, e_o, e_v, out[0]), (ixq_v, blk_v, qja_v, e_v, e_o, out[1])),
-                                   n, p, os_f, ss_f)
     t_cpu = time.perf_counter() - t_cpu0
 
     if rank != 0:
@@ -675,12 +749,6 @@ def main():
         "wall_s": {"setup": t_setup, "warmup": t_warm, "timed": ms * 1e-3, "e2e_leg": t_e2e, "cpu_leg": t_cpu,
                    "total": time.perf_counter() - t_start},
     }
-    if sharded_info is not None:
-        line["sharded"] = sharded_info
-        line["config"]["parallelism"] = "pole-sharded (ix|Q): pole blocks visit over NVLink, pairs of a block pair split by " \
-                                        "parity, one all-gather of M0/M1 and one all-reduce of [vv|vev] per sector"
-    if sampled is not None:
-        line["sampled"] = sampled
     if e2e is not None:
         line["e2e"] = e2e
     if parity is not None:
