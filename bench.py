@@ -286,9 +286,6 @@ def sharded_arm(args, o, v, n, p, torch, lib, mpi, dev, rank, world, local_rank,
     os_f, ss_f = args.os_factor, args.ss_factor
     flops_build = f_alg(o, v, n, p) + f_alg(v, o, n, p)
 
-    if args.sharded:
-        return sharded_arm(args, o, v, n, p, torch, lib, mpi, dev, rank, world, local_rank, t_start)
-
     def sync_all():
         if world > 1:
             lib.comm_barrier()
@@ -512,6 +509,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     comm = mpi.init()               # the library's NCCL communicator (one rank per process); serial when world == 1
     assert comm.size == world and comm.rank == rank
+
+    if args.sharded:
+        return sharded_arm(args, o, v, n, p, torch, lib, mpi, dev, rank, world, local_rank, t_start)
 
     def sync_all():
         if world > 1:

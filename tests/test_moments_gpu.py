@@ -358,3 +358,31 @@ def test_contexts(lib):
     st, msg = lib.sticky_status(clear=True)
     assert st != 0 and "build_part_loop_rhf" in msg and (vv == 7.0).all() and (vev == 7.0).all()
     assert lib.sticky_status()[0] == 0
+
+
+@pytest.mark.parametrize("shape", [(12, 30, 100, 42, 1.0, 1.0), (23, 17, 150, 141, 1.2, 1.0 / 3.0), (9, 40, 64, 264, 0.5, 0.0)])
+def test_pole_sharded_entry_point_single_rank(lib, shape):
+    """The pole-sharded entry point on a context without a communicator (one rank holds the only block): the
+    own-block schedule in sub-blocks of one pole, the Coulomb stage on the resident block, `+=` semantics.  The
+    multi-rank exchange itself is tests/test_multi_gpu.py (>= 2 GPUs) and tests/test_planner.py (host replay)."""
+    import torch
+    o, v, n, p, os_f, ss_f = shape
+    ixq, qja, ei, ea = orc.synth_rhf(o, v, n, p, 31)
+    dev = torch.device("cuda", 0)
+    qpad = np.zeros((n, o, v + (v & 1)))
+    qpad[:, :, :v] = qja.reshape(n, o, v)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_ixq, d_qja, d_ei, d_ea = T(ixq.reshape(o, p, n)), T(qpad), T(ei), T(ea)
+    assert lib.pole_block(o, 0, 1) == (0, o)
+    rv, rev = orc.np_build_part_loop_rhf(ixq, qja, ei, ea, p, o, v, n, 0, o, os_f, ss_f)
+    try:
+        for vis in (2 << 30, p * n * 8):
+            lib.set_option("visiting_bytes", vis)
+            out = torch.full((2, p, p), 0.125, dtype=torch.float64, device=dev)
+            lib.moments_rhf_dev_sharded(d_ixq, d_qja, d_ei, d_ea, os_factor=os_f, ss_factor=ss_f, vv=out[0], vev=out[1],
+                                        sync=True, ei_host=ei)
+            got = out.cpu().numpy() - 0.125
+            assert relerr(got[0], rv) < TOL and relerr(got[1], rev) < TOL, (shape, vis, relerr(got[0], rv), relerr(got[1], rev))
+            assert lib.last_p2p_bytes() == 0
+    finally:
+        lib.set_option("visiting_bytes", 2 << 30)
