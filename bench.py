@@ -19,7 +19,7 @@ auxgf/agf2/optragf2.py:283-293), F_alg = 1.50e15 flop.
   cpu_baseline / --impl reference : the reference's own C loop (oracle/_ref/agf2.so, built from
              /root/reference/auxgf/lib/libagf2) on the host cores, on bounded pole slices, both thread layouts
              (OpenMP over poles x serial BLAS, and one pole at a time x threaded BLAS), scaled to one build.
-Warm-up steps run 1/16 of the pair-work items of both sectors (they warm clocks, allocations and NCCL; they are not
+Warm-up steps run 1/32 of the pair-work items of both sectors (they warm clocks, allocations and NCCL; they are not
 builds); the last one runs with the two-stream overlap off and per-launch CUDA events to get the per-stage times.
 N > 1 (one process per GPU, launched by torch.distributed.run): the pair-work items are dealt round-robin to the
 ranks and ONE NCCL all-reduce of [vv|vev] per sector runs inside the library (agf2_b200_comm_*, no torch.distributed);
@@ -39,7 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DGEMM_PEAK_FALLBACK = 35.9   # TFLOP/s, cublasDgemm 8192^3 on this pool (profiles/fp64_peak_r01.json)
-WARM_PARTS = 16              # a warm-up step runs 1/16 of the pair-work items
+WARM_PARTS = 32              # a warm-up step runs 1/32 of the pair-work items
 
 
 def f_alg(o, v, n, p):
@@ -556,7 +556,7 @@ def main():
     nw = WARM_PARTS * world
 
     def warm_step(w, staged):
-        """1/16 of this rank's pair-work items of both sectors.  staged: two-stream overlap off and per-launch CUDA
+        """1/32 of this rank's pair-work items of both sectors.  staged: two-stream overlap off and per-launch CUDA
         events inside the library, so that every launch is timed alone on the GPU (with the overlap on two kernels
         share the SMs and their elapsed times add up to more than the wall time)."""
         out.zero_()
