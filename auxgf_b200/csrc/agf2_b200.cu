@@ -52,6 +52,8 @@ Options& default_options() {
         if (const char* e = getenv("AGF2_B200_THIN")) o.thin_tiles = atoi(e) != 0;
         if (const char* e = getenv("AGF2_B200_DETERMINISTIC")) o.deterministic = atoi(e) != 0;
         if (const char* e = getenv("AGF2_B200_VISITING_MB")) o.vis_bytes = (int64_t)atoll(e) << 20;
+        if (const char* e = getenv("AGF2_B200_W_EVICT_LAST")) o.w_evict_last = atoi(e) != 0;
+        if (const char* e = getenv("AGF2_B200_L2_PERSIST_MB")) o.l2_persist_bytes = (int64_t)atoll(e) << 20;
     }
     return o;
 }
@@ -103,6 +105,9 @@ int ctx_init(Ctx& c, int device) {
                                           std::to_string(prop.minor) + ", this library is built for sm_100a only");
     c.device = device;
     c.num_sms = prop.multiProcessorCount;
+    if (default_options().l2_persist_bytes > 0)
+        CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize,
+                                  (size_t)std::min<int64_t>(default_options().l2_persist_bytes, prop.persistingL2CacheMaxSize)));
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
@@ -261,8 +266,8 @@ int launch_k2(Ctx& c, K2Launch& L, int slot, cudaStream_t st) {
     c.flops[L.mode == 3 ? 2 : 1] += (double)L.total_cost / 16.0 * 2.0 * 2.0 * kTileM * kTileN * (double)kKB *
                                     L.p.nk_inner * L.p.n_outer;
     if (det && grid > 1) {
-        if (L.mode == 3) k2_fixup<true><<<grid, 256, 0, st>>>(L.p, grid);
-        else k2_fixup<false><<<grid, 256, 0, st>>>(L.p, grid);
+        if (L.mode == 3) k2_fixup<true><<<dim3(grid, kFixupParts), 256, 0, st>>>(L.p, grid);
+        else k2_fixup<false><<<dim3(grid, kFixupParts), 256, 0, st>>>(L.p, grid);
         CU_TRY(cudaGetLastError());
         count_launch(c);
     }
@@ -772,7 +777,7 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
             if (!opt.simple) {
                 k1_form<<<(unsigned)tiles.size(), kThreads, kK1SmemBytes, sc>>>(
                     mapA, mapA2 ? *mapA2 : mapA, mapB0, mapB1, c.d_t1[buf], same.ea_dev, other ? other->ea_dev : same.ea_dev,
-                    Wa, Wb, Ebuf, ldw, nk1);
+                    Wa, Wb, Ebuf, ldw, nk1, opt.w_evict_last ? kL2EvictLast : 0ull);
             } else {
                 k1_form_simple<<<(unsigned)tiles.size(), 256, 0, sc>>>(
                     ixq, ixq2 ? ixq2 : ixq, ld_ixq, (int)nphys, (int)naux, same.qja, same.ld, (int)o, (int)v,

@@ -48,6 +48,8 @@ struct Options {
     bool deterministic = true;         // stream-K partial tiles summed in a fixed order (k2_fixup)
     bool profile = true;               // CUDA events around every launch (agf2_b200_last_stage_ms)
     int64_t vis_bytes = 2ll << 30;     // pole-sharded builds: size of one visiting sub-block of (ix|Q) (two are kept)
+    bool w_evict_last = false;         // (xi|ja) workspace stores carry the L2 evict_last hint
+    int64_t l2_persist_bytes = 0;      // > 0: cudaLimitPersistingL2CacheSize set at context creation
     int64_t shard_limit = 0;           // > 0: only the first `shard_limit` sub-blocks of every ring step (benchmark sample)
 };
 Options& default_options();

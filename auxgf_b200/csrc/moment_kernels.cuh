@@ -250,7 +250,7 @@ __device__ __forceinline__ void k1_mainloop_thin(const uint8_t* __restrict__ gba
 template <int MBV>
 __device__ __forceinline__ void k1_thin_tile(const K1Tile& t, const uint8_t* __restrict__ gbase, uint32_t bar_full,
                                              uint32_t bar_empty, int nk, int warp, int lane, double* __restrict__ W0,
-                                             double* __restrict__ W1, long long ldw)
+                                             double* __restrict__ W1, long long ldw, unsigned long long w_policy)
 {
     const int gid = lane >> 2, tig = lane & 3;
     const int pg = pi8(gid);
@@ -270,13 +270,13 @@ __device__ __forceinline__ void k1_thin_tile(const K1Tile& t, const uint8_t* __r
             double2 o;
             o.x = t.p11 * acc1[mb][0] + t.p12 * acc2[mb][0];
             o.y = t.p11 * acc1[mb][1] + t.p12 * acc2[mb][1];
-            *reinterpret_cast<double2*>(Wd1 + row * ldw + t.col1 + c) = o;
+            st_hint_v2f64(Wd1 + row * ldw + t.col1 + c, o, w_policy);
         }
         if (Wd2 != nullptr && warp < nbo2) {
             double2 o;
             o.x = t.p21 * acc1[mb][0] + t.p22 * acc2[mb][0];
             o.y = t.p21 * acc1[mb][1] + t.p22 * acc2[mb][1];
-            *reinterpret_cast<double2*>(Wd2 + row * ldw + t.col2 + c) = o;
+            st_hint_v2f64(Wd2 + row * ldw + t.col2 + c, o, w_policy);
         }
     }
 }
@@ -287,7 +287,7 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
         const K1Tile* __restrict__ tiles,
         const double* __restrict__ ea0, const double* __restrict__ ea1,
         double* __restrict__ W0, double* __restrict__ W1, double* __restrict__ E0,
-        long long ldw, int nk)
+        long long ldw, int nk, unsigned long long w_policy)
 {
     extern __shared__ uint8_t smem_raw[];
     // 1024 B alignment: the swizzle pattern is a function of absolute shared-memory address bits
@@ -346,7 +346,7 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
     const int pg = pi8(gid);
     if (t.mbv > 0) {
         switch (t.mbv) {
-#define AGF2_K1_THIN(M) case M: k1_thin_tile<M>(t, gbase, bar_full, bar_empty, nk, warp, lane, W0, W1, ldw); break;
+#define AGF2_K1_THIN(M) case M: k1_thin_tile<M>(t, gbase, bar_full, bar_empty, nk, warp, lane, W0, W1, ldw, w_policy); break;
             AGF2_K1_THIN(1) AGF2_K1_THIN(2) AGF2_K1_THIN(3) AGF2_K1_THIN(4) AGF2_K1_THIN(5)
             AGF2_K1_THIN(6) AGF2_K1_THIN(7) AGF2_K1_THIN(8) AGF2_K1_THIN(9) AGF2_K1_THIN(10)
 #undef AGF2_K1_THIN
@@ -388,14 +388,14 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
                 double2 o;
                 o.x = t.p11 * acc1[mb][nb][0] + t.p12 * acc2[mb][nb][0];
                 o.y = t.p11 * acc1[mb][nb][1] + t.p12 * acc2[mb][nb][1];
-                *reinterpret_cast<double2*>(Wd1 + row * ldw + t.col1 + c) = o;
+                st_hint_v2f64(Wd1 + row * ldw + t.col1 + c, o, w_policy);
             }
             const int nbo2 = (t.p21 != 0.0) ? nb1 : nb2;   // width of out2: block 1's if it mixes block 1
             if (Wd2 != nullptr && nb < nbo2) {
                 double2 o;
                 o.x = t.p21 * acc1[mb][nb][0] + t.p22 * acc2[mb][nb][0];
                 o.y = t.p21 * acc1[mb][nb][1] + t.p22 * acc2[mb][nb][1];
-                *reinterpret_cast<double2*>(Wd2 + row * ldw + t.col2 + c) = o;
+                st_hint_v2f64(Wd2 + row * ldw + t.col2 + c, o, w_policy);
             }
         }
     }
@@ -769,6 +769,7 @@ k2_moment(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 // Adds the partial-tile slots of a k2_moment launch (grid G) into the accumulators, slot after slot in CTA order.
 // CTA b of this kernel handles the tile CTA b of k2_moment started in mid-tile, unless CTA b - 1 did so too (then
 // that CTA's fixup block walks all the slots of the tile).
+constexpr int kFixupParts = 8;     // CTAs per tile of k2_fixup (grid.y): 1024 output elements each
 template <bool kGen>
 __global__ void __launch_bounds__(256)
 k2_fixup(const __grid_constant__ K2Params p, int G)
@@ -799,20 +800,34 @@ k2_fixup(const __grid_constant__ K2Params p, int G)
     __syncthreads();
     const int n = s_n;
     const K2Tile t = p.tiles[tile];
-    for (int idx = threadIdx.x; idx < kTileM * kTileN; idx += blockDim.x) {
+    // 4 elements x 2 accumulators per thread, loads of one slot issued together (the kernel is latency bound)
+    constexpr int kPer = kTileM * kTileN / kFixupParts / 256;
+    double* d[2 * kPer];
+    double v[2 * kPer];
+    int off[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int idx = blockIdx.y * (kTileM * kTileN / kFixupParts) + j * 256 + threadIdx.x;
         const int lane = idx & 31, h = (idx >> 5) & 1, nb = (idx >> 6) & 7, mb = (idx >> 9) & 1, warp = idx >> 10;
         const int r = 16 * warp + 8 * mb + pi8(lane >> 2);
         const int c = 8 * nb + pi8(2 * (lane & 3) + h);
+        off[j] = idx;
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            double* const d = k2_out_ptr<kGen>(p, t, r, c, which);
-            if (d == nullptr) continue;
-            double v = *d;
-            for (int k = 0; k < n; ++k)
-                v += p.partial[(size_t)s_slots[k] * (2 * kTileM * kTileN) + which * (kTileM * kTileN) + idx];
-            *d = v;
+            d[2 * j + which] = k2_out_ptr<kGen>(p, t, r, c, which);
+            v[2 * j + which] = d[2 * j + which] ? *d[2 * j + which] : 0.0;
         }
     }
+    for (int k = 0; k < n; ++k) {
+        const double* slot = p.partial + (size_t)s_slots[k] * (2 * kTileM * kTileN);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+#pragma unroll
+            for (int which = 0; which < 2; ++which) v[2 * j + which] += slot[which * (kTileM * kTileN) + off[j]];
+    }
+#pragma unroll
+    for (int q = 0; q < 2 * kPer; ++q)
+        if (d[q]) *d[q] = v[q];
 }
 
 // ---- per-column weights of the Coulomb factorisation ---------------------------------------------

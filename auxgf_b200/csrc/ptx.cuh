@@ -81,6 +81,17 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
+// 16-byte global store with an L2 eviction-priority hint (policy = a createpolicy descriptor; 0: plain store).
+// The (xi|ja) workspace is written with evict_last so that the DF blocks streaming through L2 behind it do not push it
+// out to HBM before k2_moment has consumed it.
+constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;    // createpolicy.fractional.L2::evict_last, fraction 1.0
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;
+__device__ __forceinline__ void st_hint_v2f64(double* p, double2 v, unsigned long long policy) {
+    if (policy)
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+    else
+        *reinterpret_cast<double2*>(p) = v;
+}
 __device__ __forceinline__ void red_add_f64(double* p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
