@@ -5,7 +5,7 @@
 //                 (FP64 DMMA.8x8x4, operands staged by TMA into 128B-swizzled shared memory through a
 //                 4-stage mbarrier pipeline), then the fused epilogue
 //                     out1 = p11*acc1 + p12*acc2,  out2 = p21*acc1 + p22*acc2
-//                 written to the L2-resident workspace W[x][col] together with the energy weights
+//                 written to the L2-sized workspace W[x][col] together with the energy weights
 //                 E[col] = e_i + e_j - e_a.  For a pole pair i>j, (acc1, acc2) = (X_ij, X_ji) and
 //                 out1 = sqrt(ss) (X_ij - X_ji)  [all-pairs route: also out2 = sqrt(os/2) (X_ij + X_ji)]:
 //                 the 2(xi|ja)-(xj|ia) exchange combination in pair-symmetric (SYRK) form, each integral
