@@ -37,7 +37,7 @@ int fail(int code, const std::string& msg);
 
 // ---- tuning / debug options (process defaults are shared by the per-device default contexts) --------------
 struct Options {
-    int64_t ws_bytes = 40ll << 20;     // (xi|ja) workspace per ring buffer
+    int64_t ws_bytes = 384ll << 20;    // (xi|ja) workspace per ring buffer (upper bound: small calls allocate what they need)
     bool simple = false;               // naive debug kernels
     bool lpt_order = true;             // k1_form tiles of a chunk launched longest first
     bool tune_chunk = true;            // chunk size chosen for whole waves of k1_form tiles

@@ -115,7 +115,7 @@ inline std::vector<ShardStep> shard_steps(int64_t o, int64_t rank, int64_t R, in
 }
 
 struct PlanConfig {
-    int64_t ws_bytes = 40ll << 20;   // workspace per ring buffer
+    int64_t ws_bytes = 384ll << 20;  // workspace per ring buffer (upper bound)
     int num_sms = 148;
     bool simple = false;             // naive debug kernels: all-pairs route, no tuning, no thin tiles
     bool lpt_order = true;           // k1_form tiles of a chunk launched longest first
@@ -228,6 +228,14 @@ struct MomentPlan {
         blk_same = split_blocks(vpad);
         blk_other = split_blocks(vbpad);
         for (int k = 0; k < 4; ++k) chunk_items[k] = 0;
+        if (!sharded) {
+            // a call never needs more workspace columns than all of its items together
+            int64_t need = 0;
+            for (const Item& it : sym_items)
+                need += it.kind == 2 ? vbpad : (it.kind == 1 ? ((ca != 0.0) + (cs != 0.0)) * vpad : vpad);
+            need = std::max<int64_t>(need, (int64_t)asym_items.size() * vpad);
+            cap_cols = std::min(cap_cols, rup(std::max<int64_t>(need, 2 * std::max(vpad, vbpad)), 16));
+        }
         return 0;
     }
 

@@ -208,7 +208,9 @@ int agf2_b200_host_register(const void *ptr, int64_t bytes);
 int agf2_b200_host_unregister(const void *ptr);
 
 /* Workspace for the (xi|ja) chunk that flows between the two kernels, in bytes per buffer
- * (two buffers are kept).  Default 40 MiB each so that both stay resident in the 126 MB L2. */
+ * (a ring of buffers per stream is kept; a call allocates no more than its work items need).  Default 384 MiB:
+ * long chunks amortise launch tails and the stream-K prologue/epilogue; the chunk streams through L2 either way
+ * (measured: profiles/r02k_workspace_sweep.log, r02f_l2_k1_k2_nocachectl.csv). */
 int agf2_b200_set_workspace_bytes(int64_t bytes);
 
 /* Host-memory variants with SCS factors and 64-bit sizes (copies inputs to HBM, runs, adds the
