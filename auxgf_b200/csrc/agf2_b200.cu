@@ -792,7 +792,8 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
             c.last_plan[5]++;
             {   // executed DMMA flops of the launch (padding rows / columns included)
                 double units = 0.0;
-                for (const K1Tile& t : tiles) units += (t.mbv > 0 ? 8.0 * t.mbv : (double)kTileM) * 8.0 * (t.nb1 + t.nb2);
+                for (const K1Tile& t : tiles)
+                    units += (t.mbv > 10 ? 16.0 * ((t.mbv + 1) / 2) : (t.mbv > 0 ? 8.0 * t.mbv : (double)kTileM)) * 8.0 * (t.nb1 + t.nb2);
                 c.flops[0] += 2.0 * units * (double)kKB * nk1;
             }
 

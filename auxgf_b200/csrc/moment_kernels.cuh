@@ -48,7 +48,8 @@ struct K1Tile {
     long long col1, col2;  // destination column of out1 / out2
     double p11, p12, p21, p22;
     double e1, e2;         // e_i + e_j of out1 / out2
-    int mbv;               // > 0: thin tile -- only the first mbv 8-row blocks of the x-block exist (see k1_mainloop_thin)
+    int mbv;               // > 0: only the first mbv 8-row blocks of the x-block exist: thin tile (<= 10, k1_mainloop_thin)
+                           // or quad tile (11..14, k1_quad_tile)
     int asel1, asel2;      // which (ix|Q) tensor i1 / i2 index: 0 the resident one, 1 the visiting pole block (pole-sharded
     int pad_;              // builds: ixq is split over the GPUs and blocks of poles travel over NVLink)
 };
@@ -281,6 +282,118 @@ __device__ __forceinline__ void k1_thin_tile(const K1Tile& t, const uint8_t* __r
     }
 }
 
+// Quad tile: the ragged last x-block with 11..14 valid 8-row blocks (e.g. nphys = 367: 111 rows).  The thin mapping
+// would need all MBV A fragments of both integral blocks in registers; here the 8 warps form a 2 x 4 grid instead --
+// warp (r, c) takes the row blocks [r MBW, (r+1) MBW), MBW = ceil(MBV / 2), and the column blocks 2c, 2c+1 of BOTH
+// integral blocks (the fused epilogue needs both in the same thread) -- so the tile costs 2 MBW / 16 of a full one
+// when nb = 8.  One pipeline stage = 4 units (ks, set) of up to 4 MBW DMMAs; unit u+1's fragments (the other set) are
+// loaded while unit u's DMMAs issue.  Shared-memory traffic per DMMA is that of the full mapping.
+template <int MBW>
+__device__ __forceinline__ void k1_quad_tile(const K1Tile& t, const uint8_t* __restrict__ gbase, uint32_t bar_full,
+                                             uint32_t bar_empty, int nk, int warp, int lane, double* __restrict__ W0,
+                                             double* __restrict__ W1, long long ldw, unsigned long long w_policy)
+{
+    const int gid = lane >> 2, tig = lane & 3;
+    const int pg = pi8(gid);
+    const int r = warp >> 2, c = warp & 3;
+    const int mb0 = r * MBW;
+    // column blocks of this warp inside each integral block
+    const int n1 = min(2, max(0, t.nb1 - 2 * c)), n2 = min(2, max(0, t.nb2 - 2 * c));
+    const uint32_t a_off[2] = {(uint32_t)((8 * mb0 + pg) * 128 + (((tig) ^ pg) << 4)),
+                               (uint32_t)((8 * mb0 + pg) * 128 + (((4 + tig) ^ pg) << 4))};
+    uint32_t b_off[2][2];   // [j][e]: column block 2c + j (parity j), K row 2 tig + e
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int kr = 2 * tig + e;
+            const int chunk = 4 * j + (gid >> 1);
+            b_off[j][e] = (uint32_t)(kr * 128 + ((chunk ^ kr) << 4) + (gid & 1) * 8 + c * 2048);
+        }
+    double acc[2][MBW][2][2];   // [set][mb][j][half]
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int m = 0; m < MBW; ++m)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[s][m][j][0] = acc[s][m][j][1] = 0.0;
+    double2 fa[2][MBW];     // [set][mb]
+    double fb[2][2][2];     // [set][e][j]
+    auto load_unit = [&](const uint8_t* st, int u) {
+        const int ks = u >> 1, set = u & 1;
+        const int n = set ? n2 : n1;
+        if (n > 0) {
+#pragma unroll
+            for (int m = 0; m < MBW; ++m)
+                fa[set][m] = *reinterpret_cast<const double2*>(st + set * 16384 + a_off[ks] + m * 1024);
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (j < n) fb[set][e][j] = *reinterpret_cast<const double*>(st + 32768 + set * 8192 + b_off[j][e] + ks * 1024);
+        }
+    };
+    auto compute_unit = [&](int u) {
+        const int set = u & 1;
+        const int n = set ? n2 : n1;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (j < n) {
+#pragma unroll
+                    for (int m = 0; m < MBW; ++m) {
+                        const double a = e ? fa[set][m].y : fa[set][m].x;
+                        if (set) dmma884(acc[1][m][j][0], acc[1][m][j][1], a, fb[1][e][j]);
+                        else dmma884(acc[0][m][j][0], acc[0][m][j][1], a, fb[0][e][j]);
+                    }
+                }
+    };
+    mbar_wait(bar_full, 0);
+    load_unit(gbase, 0);
+    for (int it = 0; it < nk; ++it) {
+        const int s = it % kK1Stages;
+        const uint8_t* st = gbase + s * kK1StageBytes;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (u < 3) {
+                load_unit(st, u + 1);
+            } else if (it + 1 < nk) {
+                const int s2 = (it + 1) % kK1Stages;
+                mbar_wait(bar_full + 8 * s2, ((it + 1) / kK1Stages) & 1);
+                load_unit(gbase + s2 * kK1StageBytes, 0);
+            }
+            compute_unit(u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+    double* const Wd1 = t.ws1 == 0 ? W0 : (t.ws1 == 1 ? W1 : nullptr);
+    double* const Wd2 = t.ws2 == 0 ? W0 : (t.ws2 == 1 ? W1 : nullptr);
+    const int nbo2 = (t.p21 != 0.0) ? t.nb1 : t.nb2;
+#pragma unroll
+    for (int m = 0; m < MBW; ++m) {
+        const long long row = (long long)t.xb * kTileM + 8 * (mb0 + m) + pg;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int nb = 2 * c + j;
+            const int col = 8 * nb + 2 * tig;
+            if (Wd1 != nullptr && nb < t.nb1) {
+                double2 o;
+                o.x = t.p11 * acc[0][m][j][0] + t.p12 * acc[1][m][j][0];
+                o.y = t.p11 * acc[0][m][j][1] + t.p12 * acc[1][m][j][1];
+                st_hint_v2f64(Wd1 + row * ldw + t.col1 + col, o, w_policy);
+            }
+            if (Wd2 != nullptr && nb < nbo2) {
+                double2 o;
+                o.x = t.p21 * acc[0][m][j][0] + t.p22 * acc[1][m][j][0];
+                o.y = t.p21 * acc[0][m][j][1] + t.p22 * acc[1][m][j][1];
+                st_hint_v2f64(Wd2 + row * ldw + t.col2 + col, o, w_policy);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
         const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -350,6 +463,8 @@ k1_form(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtens
             AGF2_K1_THIN(1) AGF2_K1_THIN(2) AGF2_K1_THIN(3) AGF2_K1_THIN(4) AGF2_K1_THIN(5)
             AGF2_K1_THIN(6) AGF2_K1_THIN(7) AGF2_K1_THIN(8) AGF2_K1_THIN(9) AGF2_K1_THIN(10)
 #undef AGF2_K1_THIN
+            case 11: case 12: k1_quad_tile<6>(t, gbase, bar_full, bar_empty, nk, warp, lane, W0, W1, ldw, w_policy); break;
+            case 13: case 14: k1_quad_tile<7>(t, gbase, bar_full, bar_empty, nk, warp, lane, W0, W1, ldw, w_policy); break;
             default: __trap();
         }
         k1_write_weights(t, warp, gid, tig, ea0, ea1, E0);

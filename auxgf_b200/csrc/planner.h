@@ -120,7 +120,7 @@ struct PlanConfig {
     bool simple = false;             // naive debug kernels: all-pairs route, no tuning, no thin tiles
     bool lpt_order = true;           // k1_form tiles of a chunk launched longest first
     bool tune_chunk = true;          // chunk size chosen for whole waves of k1_form tiles
-    bool thin_tiles = true;          // last x-block with <= 80 valid rows uses the thin-tile mapping
+    bool thin_tiles = true;          // ragged last x-block: thin-tile (<= 80 rows) or quad-tile (81..112 rows) mapping
     bool coulomb = true;             // Coulomb factorisation allowed ...
     bool coulomb_auto = true;        // ... and chosen per call by a flop estimate
 };
@@ -265,13 +265,17 @@ struct MomentPlan {
     int thin_mbv(int xb, int nb1, int nb2) const {
         if (!cfg.thin_tiles || cfg.simple || xb != nxb - 1) return 0;
         const int mbv = (int)((nphys - (int64_t)xb * kTileM + 7) / 8);
-        if (mbv > 10) return 0;
+        if (mbv > 14) return 0;
         const int nsets = (nb1 > 0) + (nb2 > 0);
+        if (mbv > 10)   // quad tile (2 x 4 warp grid): ceil(mbv / 2) row blocks x 2 column blocks of each integral block
+            return (1.03 * ((mbv + 1) / 2) * 2 * nsets < 2.0 * (nb1 + nb2)) ? mbv : 0;
         return (1.15 * mbv * nsets < 2.0 * (nb1 + nb2)) ? mbv : 0;   // per-warp DMMA count: thin vs full
     }
     // per-warp DMMAs per k-step (x 2): the tile's duration
     static int tile_work(const K1Tile& t) {
-        return t.mbv > 0 ? t.mbv * ((t.nb1 > 0) + (t.nb2 > 0)) : 2 * (t.nb1 + t.nb2);
+        const int nsets = (t.nb1 > 0) + (t.nb2 > 0);
+        if (t.mbv > 10) return ((t.mbv + 1) / 2) * 2 * nsets;
+        return t.mbv > 0 ? t.mbv * nsets : 2 * (t.nb1 + t.nb2);
     }
 
     int items_per_chunk(int kind) {
@@ -289,14 +293,14 @@ struct MomentPlan {
                 for (int xb = 0; xb < nxb; ++xb)
                     for (auto& b : blks) {
                         const int mbv = thin_mbv(xb, b.second, b.second);
-                        t.push_back((mbv ? (double)mbv : 2.0 * b.second) + ovh);
+                        t.push_back((mbv > 10 ? 2.0 * ((mbv + 1) / 2) : (mbv ? (double)mbv : 2.0 * b.second)) + ovh);
                     }
             } else {
                 // plain blocks pair up two by two across items: model one item as half-tiles
                 for (int xb = 0; xb < nxb; ++xb)
                     for (auto& b : blks) {
                         const int mbv = thin_mbv(xb, b.second, b.second);
-                        t.push_back((mbv ? 0.5 * mbv : (double)b.second) + 0.5 * ovh);
+                        t.push_back((mbv > 10 ? (double)((mbv + 1) / 2) : (mbv ? 0.5 * mbv : (double)b.second)) + 0.5 * ovh);
                     }
             }
             n = pick_chunk_items(t, n_max, cfg.num_sms, cfg.lpt_order, 0.5);

@@ -95,6 +95,28 @@ def test_thin_tiles(lib):
         lib.set_coulomb_factorization(2)
 
 
+def test_quad_tiles(lib):
+    """Last x-block with 11..14 valid 8-row blocks (k1_quad_tile<6>, <7>: 2 x 4 warp grid), alone and behind full
+    x-blocks; 64-column blocks (where the mapping is chosen) next to narrower ones; both routes; slice; UHF; and the
+    planner really emits such tiles for these shapes."""
+    for p_ in (8 * 11 - 5, 8 * 12, 8 * 13 - 1, 8 * 14 - 7, 128 + 8 * 12 - 2, 256 + 111):
+        _check_rhf(lib, 5, 128, 90, p_, seed=50 + p_ % 7)
+        _check_rhf(lib, 4, 100, 50, p_, seed=60 + p_ % 5)
+    st = lib.plan_stats(367, 10, 128, 400)
+    assert st["thin_tiles"] > 0
+    _check_rhf(lib, 6, 64, 40, 128 + 100, seed=44, i0=1, i1=4, os_f=1.2, ss_f=1.0 / 3.0)
+    args = orc.synth_uhf(5, 66, 4, 71, 60, 111, 6)
+    rv, rev = orc.np_build_part_loop_uhf(*args, 111, 5, 4, 66, 71, 60, 0, 5)
+    for mode in (2, 0):                   # 0: DIAG / OS items (single-block and paired plain tiles) through quad tiles
+        lib.set_coulomb_factorization(mode)
+        try:
+            vv, vev = lib.moments_uhf(*args, 111)
+            assert relerr(vv, rv) < TOL and relerr(vev, rev) < TOL
+            _check_rhf(lib, 5, 130, 90, 128 + 105, seed=45)
+        finally:
+            lib.set_coulomb_factorization(2)
+
+
 def test_reference_drop_in_symbols(lib):
     """The void symbols with the reference's exact signature (optragf2.c:32-43, optuagf2.c:31-47)."""
     o, v, n, p = 6, 21, 50, 30
