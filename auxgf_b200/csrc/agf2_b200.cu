@@ -233,7 +233,8 @@ struct K2Launch {
     CUtensorMap a0, a1, b;
     K2Params p;
     int mode;          // 0: moments (W W^T), 1: M build (two weight vectors), 2: Coulomb step (two A operands), 3: GEMM
-    long long total_cost;    // cost_prefix[ntiles]
+    long long total_cost;    // cost_prefix[ntiles] (time model, sixteenths of a full tile)
+    long long total_work = -1;   // executed DMMA work in the same unit (-1: equal to total_cost)
 };
 
 K2Params k2_params() {
@@ -263,7 +264,7 @@ int launch_k2(Ctx& c, K2Launch& L, int slot, cudaStream_t st) {
     CU_TRY(cudaGetLastError());
     count_launch(c);
     // executed DMMA flops: two 128 x 64 accumulators per full tile, K padded to whole 16-element stages
-    c.flops[L.mode == 3 ? 2 : 1] += (double)L.total_cost / 16.0 * 2.0 * 2.0 * kTileM * kTileN * (double)kKB *
+    c.flops[L.mode == 3 ? 2 : 1] += (double)(L.total_work >= 0 ? L.total_work : L.total_cost) / 16.0 * 2.0 * 2.0 * kTileM * kTileN * (double)kKB *
                                     L.p.nk_inner * L.p.n_outer;
     if (det && grid > 1) {
         if (L.mode == 3) k2_fixup<true><<<dim3(grid, kFixupParts), 256, 0, st>>>(L.p, grid);
@@ -428,7 +429,7 @@ struct SmallTables {
     }
 };
 
-struct SymTiles { const K2Tile* tiles; const int* cost; int ntiles; int total_cost; };
+struct SymTiles { const K2Tile* tiles; const int* cost; int ntiles; int total_cost; long long total_work; };
 
 int comm_allgather(Ctx& c, double* buf, int64_t count_per_rank, cudaStream_t st);
 
@@ -448,7 +449,7 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, int64_t ixq_poles, co
                 int64_t nphys, int64_t naux, int64_t istart, int64_t iend, double w_same_in, double w_same_out,
                 double w_other, int64_t part, int64_t nparts, bool gather, int64_t pole_off, double* S_vv, double* S_vev,
                 int64_t p_pad, const SymTiles& sym, const K2Tile* d_tm, const int* d_cm, int nt_m, int cost_m,
-                cudaStream_t st)
+                long long work_m, cudaStream_t st)
 {
     struct Pass { const Spin* sp; double w_in, w_out; };
     std::vector<Pass> passes;
@@ -496,6 +497,7 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, int64_t ixq_poles, co
         L.a1 = L.a0; L.b = L.a0;
         L.mode = 1;
         L.total_cost = cost_m;
+        L.total_work = work_m;
         K2Params p = k2_params();
         p.w0 = c.wq[0].p; p.w1 = c.wq[1].p; p.tiles = d_tm; p.cost_prefix = d_cm;
         p.acc_vv = Mt0; p.acc_vev = Mt1; p.ldacc = ldm;
@@ -558,6 +560,7 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, int64_t ixq_poles, co
             L.b = mapIx;
             L.mode = 2;
             L.total_cost = sym.total_cost;
+            L.total_work = sym.total_work;
             K2Params p = k2_params();
             p.w1 = c.we.p; p.tiles = sym.tiles; p.cost_prefix = sym.cost;
             p.acc_vv = S_vv; p.acc_vev = S_vev; p.ldacc = p_pad;
@@ -691,8 +694,15 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
             if (kTileN * yb + kTileN - 1 >= kTileM * xb) t2_sym.push_back({xb, yb, 0, 0});
         }
     std::vector<int> cost_sym(1, 0), cost_all(1, 0), cost_m(1, 0);
-    for (const K2Tile& t : t2_sym) cost_sym.push_back(cost_sym.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 1, 1));
-    for (const K2Tile& t : t2_all) cost_all.push_back(cost_all.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 0, 1));
+    long long work_sym = 0, work_all = 0, work_m = 0;
+    for (const K2Tile& t : t2_sym) {
+        cost_sym.push_back(cost_sym.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 1, 1));
+        work_sym += k2_tile_work(t.xb, t.yb, (int)nphys, (int)nphys, 1, 1);
+    }
+    for (const K2Tile& t : t2_all) {
+        cost_all.push_back(cost_all.back() + k2_tile_cost(t.xb, t.yb, (int)nphys, (int)nphys, 0, 1));
+        work_all += k2_tile_work(t.xb, t.yb, (int)nphys, (int)nphys, 0, 1);
+    }
     if (fact) {     // tiles of this part's block of M rows
         const int64_t ntq = (naux + kTileM - 1) / kTileM;
         const int64_t q_lo = ntq * m_part / m_nparts * kTileM;
@@ -705,6 +715,7 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
                 if (msym && kTileN * yb + kTileN - 1 < kTileM * xb) continue;
                 t2_m.push_back({xb, yb, 0, 0});
                 cost_m.push_back(cost_m.back() + k2_tile_cost(xb, yb, (int)nq, (int)naux, msym, 1));
+                work_m += k2_tile_work(xb, yb, (int)nq, (int)naux, msym, 1);
             }
     }
     SmallTables small(c);
@@ -813,6 +824,7 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
                 L.a1 = L.a0;
                 L.mode = 0;
                 L.total_cost = sym ? cost_sym.back() : cost_all.back();
+                L.total_work = sym ? work_sym : work_all;
                 K2Params p = k2_params();
                 p.w1 = Ebuf; p.tiles = sym ? d_t2_sym : d_t2_all; p.cost_prefix = sym ? d_cost_sym : d_cost_all;
                 p.acc_vv = a_vv; p.acc_vev = a_vev; p.ldacc = p_pad;
@@ -910,15 +922,15 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         if (gate) rc = gate_wait(gate, (int)(iend - istart) - 1, st);
         // weights of the Coulomb-type terms: same-spin tensor (c - s) [+ s for j outside the slice], other spin os
         if (!rc) {
-            const SymTiles symt{d_t2_sym, d_cost_sym, (int)t2_sym.size(), cost_sym.back()};
+            const SymTiles symt{d_t2_sym, d_cost_sym, (int)t2_sym.size(), cost_sym.back(), work_sym};
             if (sh)
                 rc = run_coulomb(c, ixq, ld_ixq, n_res, same, nullptr, nphys, naux, 0, n_res, c_same - s_same, c_same, 0.0,
                                  sh->rank, sh->nranks, true, shard_lo(o, sh->rank, sh->nranks), c.acc.p, c.acc.p + acc_n,
-                                 p_pad, symt, d_t2_m, d_cost_m, (int)t2_m.size(), cost_m.back(), st);
+                                 p_pad, symt, d_t2_m, d_cost_m, (int)t2_m.size(), cost_m.back(), work_m, st);
             else
                 rc = run_coulomb(c, ixq, ld_ixq, o, same, other, nphys, naux, istart, iend, c_same - s_same, c_same,
                                  os_other, part, nparts, false, 0, c.acc.p, c.acc.p + acc_n, p_pad, symt, d_t2_m, d_cost_m,
-                                 (int)t2_m.size(), cost_m.back(), st);
+                                 (int)t2_m.size(), cost_m.back(), work_m, st);
         }
     }
     // join the second chain (also on error paths: nothing may be left in flight behind the caller's back)

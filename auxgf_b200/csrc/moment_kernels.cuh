@@ -581,23 +581,36 @@ __host__ __device__ inline void k2_warp_range(int xb, int yb, int warp, int rows
     if (lo >= hi) lo = hi = 0;
     else { lo = 0; hi = 8; }      // a warp either computes all 8 column blocks or skips the tile
 }
-// Cost of a tile in sixteenths of a full one: the busiest SM sub-partition (warps w and w + 4 share one).
-// A partially masked warp still issues its predicated-off DMMAs, so it never costs less than half a full one;
-// a fully masked warp branches over the unit.
+// Time of a tile in sixteenths of a full one (what stream-K balances): the slowest SM sub-partition (warps w and
+// w + 4 share one; a fully masked warp branches over the unit).  A sub-partition with ONE active warp does not run at
+// half the time of one with two: a single warp issues DMMA.8x8x4 at ~57 % of the pipe rate (measured: the SM whose
+// stream-K range held the diagonal tiles executed 62 % of the average flops in 111 % of the average time,
+// profiles/r02_k2_moment_ncu.csv), so it costs 14, not 8.
 __host__ __device__ inline int k2_tile_cost(int xb, int yb, int rows_valid, int cols_valid, int sym, int mask)
 {
     int worst = 0;
     for (int s = 0; s < 4; ++s) {
-        int sum = 0;
+        int active = 0;
         for (int w = s; w < 8; w += 4) {
             int lo, hi;
             k2_warp_range(xb, yb, w, rows_valid, cols_valid, sym, mask, lo, hi);
-            const int n = hi - lo;
-            sum += n == 0 ? 0 : (n < 4 ? 4 : n);
+            active += hi > lo ? 1 : 0;
         }
-        worst = sum > worst ? sum : worst;
+        const int t = active == 2 ? 16 : (active == 1 ? 14 : 0);
+        worst = t > worst ? t : worst;
     }
     return worst < 4 ? 4 : worst;   // shared-memory traffic and barriers do not shrink with the mask
+}
+// DMMA work of a tile in sixteenths of a full one (executed-flop accounting): two per active warp
+__host__ __device__ inline int k2_tile_work(int xb, int yb, int rows_valid, int cols_valid, int sym, int mask)
+{
+    int active = 0;
+    for (int w = 0; w < 8; ++w) {
+        int lo, hi;
+        k2_warp_range(xb, yb, w, rows_valid, cols_valid, sym, mask, lo, hi);
+        active += hi > lo ? 1 : 0;
+    }
+    return 2 * active;
 }
 
 // stream-K boundary b of G: position (tile, kit) at cost  total * b / G
