@@ -384,6 +384,7 @@ struct PoleGate {
     const std::vector<cudaEvent_t>* ev;
     std::atomic<int>* ready;
     std::atomic<int>* failed;
+    bool with_qja = false;     // the (Q|ja) columns of a pole travel with it: the Coulomb stage then needs every pole
 };
 
 int gate_wait(const PoleGate* gate, int need_rank, cudaStream_t sc) {
@@ -919,7 +920,7 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
     }
     if (!rc && fact) {
         // host-pointer API: every pole of the slice must have landed
-        if (gate) rc = gate_wait(gate, (int)(iend - istart) - 1, st);
+        if (gate) rc = gate_wait(gate, gate->with_qja ? (int)o - 1 : (int)(iend - istart) - 1, st);
         // weights of the Coulomb-type terms: same-spin tensor (c - s) [+ s for j outside the slice], other spin os
         if (!rc) {
             const SymTiles symt{d_t2_sym, d_cost_sym, (int)t2_sym.size(), cost_sym.back(), work_sym};

@@ -36,8 +36,12 @@ struct Uploader {
     PoleGate g;
     std::string error;
 
+    // host_q (optional; only without a communicator): (Q|ja) is not staged up front but travels with the poles -- pole i
+    // brings its columns qja[:, i, :] (naux rows of nvir doubles) along, so that the pair loop starts after the first
+    // two poles instead of after the whole tensor
     int start(Ctx& c, const double* host, int slot, int64_t nocc, int64_t nphys, int64_t naux, int64_t istart,
-              int64_t iend, bool shard, int64_t* ld_out) {
+              int64_t iend, bool shard, int64_t* ld_out, const double* host_q = nullptr, double* dev_q = nullptr,
+              int64_t nvir = 0, int64_t ld_q = 0) {
         const int64_t ld = rup(naux, 2);
         if (int r = grow(c.stage[slot], (size_t)std::max<int64_t>(nocc * nphys * ld, 2), false)) return r;
         *ld_out = ld;
@@ -52,7 +56,7 @@ struct Uploader {
         for (int64_t i = iend; i < nocc; ++i) order.push_back((int)i);
         rank.assign((size_t)nocc, 0);
         for (size_t k = 0; k < order.size(); ++k) rank[order[k]] = (int)k;
-        g.rank = &rank; g.ev = &c.pole_ev; g.ready = &ready; g.failed = &failed;
+        g.rank = &rank; g.ev = &c.pole_ev; g.ready = &ready; g.failed = &failed; g.with_qja = host_q != nullptr;
         double* dev = c.stage[slot].p;
         const int device = c.device;
         cudaStream_t cs = c.copy_stream;
@@ -65,8 +69,12 @@ struct Uploader {
         th = std::thread([=]() {
             if (cudaSetDevice(device) != cudaSuccess) { failed.store(1); return; }
             auto copy_pole = [&](int64_t i) {
-                return cudaMemcpy2DAsync(dev + i * pole, ld * 8, host + i * nphys * naux, naux * 8, naux * 8, nphys,
-                                         cudaMemcpyHostToDevice, cs);
+                cudaError_t e = cudaMemcpy2DAsync(dev + i * pole, ld * 8, host + i * nphys * naux, naux * 8, naux * 8, nphys,
+                                                  cudaMemcpyHostToDevice, cs);
+                if (e == cudaSuccess && host_q)
+                    e = cudaMemcpy2DAsync(dev_q + i * ld_q, nocc * ld_q * 8, host_q + i * nvir, nocc * nvir * 8, nvir * 8,
+                                          naux, cudaMemcpyHostToDevice, cs);
+                return e;
             };
             size_t k = 0;
             while (k < order.size()) {
@@ -182,8 +190,13 @@ int host_rhf(Ctx& c, const double* ixq, const double* qja, const double* ei, con
     if (multi) { part = c.rank; nparts = c.nranks; }
     c.last_comm_bytes[0] = c.last_comm_bytes[1] = c.last_comm_bytes[2] = 0;
     int64_t ld_ixq, ld_qja, ld1;
-    // qja travels on the copy stream too: with a communicator its all-gather must precede the uploader's on every rank
-    if (int r = stage_in(c, 1, qja, naux * nocc, nvir, &ld_qja, multi, c.copy_stream)) return r;   // (naux*nocc) rows of nvir
+    // qja travels on the copy stream too: with a communicator its all-gather must precede the uploader's on every rank;
+    // without one its columns ride along with the poles of ixq (Uploader)
+    const bool q_with_poles = !multi;
+    if (q_with_poles) {
+        ld_qja = rup(nvir, 2);
+        if (int r = grow(c.stage[1], (size_t)std::max<int64_t>(naux * nocc * ld_qja, 2), false)) return r;
+    } else if (int r = stage_in(c, 1, qja, naux * nocc, nvir, &ld_qja, multi, c.copy_stream)) return r;   // (naux*nocc) rows of nvir
     if (int r = stage_in(c, 2, ei, 1, nocc, &ld1, false, c.copy_stream)) return r;
     if (int r = stage_in(c, 3, ea, 1, nvir, &ld1, false, c.copy_stream)) return r;
     CU_TRY(cudaEventRecord(c.ev_copy, c.copy_stream));
@@ -193,7 +206,9 @@ int host_rhf(Ctx& c, const double* ixq, const double* qja, const double* ei, con
     double* dvv = c.stage[4].p;
     double* dvev = c.stage[4].p + nphys * nphys;
     Uploader up;      // ixq streams in pole by pole while the first pairs are already being processed
-    if (int r = up.start(c, ixq, 0, nocc, nphys, naux, istart, iend, multi, &ld_ixq)) return r;
+    if (int r = up.start(c, ixq, 0, nocc, nphys, naux, istart, iend, multi, &ld_ixq, q_with_poles ? qja : nullptr,
+                         c.stage[1].p, nvir, ld_qja))
+        return r;
     int r = moments_rhf_impl(c, c.stage[0].p, ld_ixq, c.stage[1].p, ld_qja, c.stage[2].p, c.stage[3].p, ei, nphys, nocc,
                              nvir, naux, istart, iend, os_factor, ss_factor, part, nparts, dvv, dvev, st, 0, &up.g, false);
     up.join();

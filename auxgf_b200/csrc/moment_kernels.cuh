@@ -5,17 +5,19 @@
 //                 (FP64 DMMA.8x8x4, operands staged by TMA into 128B-swizzled shared memory through a
 //                 4-stage mbarrier pipeline), then the fused epilogue
 //                     out1 = p11*acc1 + p12*acc2,  out2 = p21*acc1 + p22*acc2
-//                 written to the L2-sized workspace W[x][col] together with the energy weights
+//                 written to the chunk workspace W[x][col] together with the energy weights
 //                 E[col] = e_i + e_j - e_a.  For a pole pair i>j, (acc1, acc2) = (X_ij, X_ji) and
 //                 out1 = sqrt(ss) (X_ij - X_ji)  [all-pairs route: also out2 = sqrt(os/2) (X_ij + X_ji)]:
 //                 the 2(xi|ja)-(xj|ia) exchange combination in pair-symmetric (SYRK) form, each integral
-//                 formed once.  A ragged last x-block (<= 80 valid rows) uses the thin-tile warp mapping
-//                 (k1_mainloop_thin).  Replaces auxgf/lib/libagf2/optragf2.c:121-199.
+//                 formed once.  A ragged last x-block uses the thin-tile (<= 80 valid rows, k1_mainloop_thin) or
+//                 quad-tile (81..112 rows, k1_quad_tile) warp mapping.  Replaces auxgf/lib/libagf2/optragf2.c:121-199.
 //   k2_moment   : acc_vv += A' B^T, acc_vev += A'' B^T on 128 x 64 output tiles, stream-K over the SMs (same
-//                 DMMA/TMA pipeline; weights applied to the A fragments in registers), reduced into the
-//                 accumulators with red.global.add.f64.  Three uses: pair-loop moments W W^T / W diag(E) W^T
+//                 DMMA/TMA pipeline; weights applied to the A fragments in registers).  The segment that starts a
+//                 tile adds into the accumulators, every other segment goes to a per-CTA slot that k2_fixup adds in
+//                 CTA order (bit-reproducible sums).  Uses: pair-loop moments W W^T / W diag(E) W^T
 //                 (optragf2.c:206-290, upper-triangle tiles only), the M0/M1 build and the Coulomb step of the
-//                 Coulomb factorisation (see the comment above the kernel).
+//                 Coulomb factorisation (see the comment above the kernel), and -- kGen -- the general GEMM behind
+//                 T = ixq [M0|M1], the DF transform, DF-JK and the two-body energy.
 //   k3_finalize : mirrors the upper triangle, adds the non-symmetric part, accumulates into vv/vev.
 //   *_simple    : naive one-thread-per-element versions of k1/k2 driven by the same tile lists (debug).
 #pragma once
