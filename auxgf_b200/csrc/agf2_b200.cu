@@ -580,6 +580,8 @@ int run_coulomb(Ctx& c, const double* ixq, int64_t ld_ixq, int64_t ixq_poles, co
 struct Reduce { bool on = false; };
 
 int comm_allreduce_sum(Ctx& c, double* buf, int64_t count, cudaStream_t st);
+int comm_allreduce(Ctx& c, double* buf, int64_t count, int op, cudaStream_t st);
+constexpr int kNcclMaxOp = 2;      // ncclMax
 int comm_sendrecv(Ctx& c, const double* sendbuf, int64_t send_count, int dst, double* recvbuf, int64_t recv_count, int src,
                   cudaStream_t st);
 
@@ -858,6 +860,21 @@ int run_moments(Ctx& c, const double* ixq, int64_t ld_ixq, const Spin& same, con
         int64_t nb_max = 0;
         for (int64_t r = 0; r < R; ++r) nb_max = std::max(nb_max, shard_lo(o, r + 1, R) - shard_lo(o, r, R));
         const int64_t sb = shard_sub_block(*c.opt, nb_max, pole_elems);
+        if (R > 1) {
+            // every rank must walk the same schedule: a different sub-block size or sample limit on one rank would
+            // leave unmatched sends / receives behind (a hang, not an error) -- compare them first
+            double chk[6] = {(double)sb, -(double)sb, (double)c.opt->shard_limit, -(double)c.opt->shard_limit, (double)o, -(double)o};
+            if (int r = grow(c.packed, 8, false)) return r;
+            CU_TRY(cudaMemcpyAsync(c.packed.p, chk, sizeof(chk), cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaStreamSynchronize(st));          // (chk is pageable stack memory)
+            if (int r = comm_allreduce(c, c.packed.p, 6, kNcclMaxOp, st)) return r;
+            CU_TRY(cudaMemcpyAsync(chk, c.packed.p, sizeof(chk), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (chk[0] != -chk[1] || chk[2] != -chk[3] || chk[4] != -chk[5])
+                return fail(AGF2_B200_EINVAL, "pole-sharded build: the ranks disagree on nocc, \"visiting_bytes\" or "
+                                              "\"shard_step_limit\"");
+            c.last_comm_bytes[1] = 0;                   // (not part of the build's traffic)
+        }
         const std::vector<ShardStep> steps = shard_steps(o, rk, R, sb, c.opt->shard_limit);
         CUtensorMap mapVis[2];
         if (R > 1) {

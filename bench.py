@@ -713,9 +713,11 @@ def main():
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
         traffic = rd[0] * scale[rd[1]] + wr[0] * scale[wr[1]]
-        traffic_note = ("dram read+write bytes of one k1_form launch (grid %d), %s: the DF blocks of its 39 pole pairs (the "
-                        "ixq rows are re-read once per column block, L2 hit rate ~52 %%) plus 36-75 MB of workspace "
-                        "write-back; the path is tensor-bound (18 %% of HBM peak)" % (int(m["launch__grid_size"][0]), os.path.basename(path)))
+        traffic_note = ("dram read+write bytes of one k1_form launch (grid %d CTAs), %s: the DF blocks of the launch's pole "
+                        "pairs (ixq rows re-read once per column block, L2 hit rate %.0f %%) plus the workspace write-back; the "
+                        "path is tensor-bound (%.0f %% of HBM peak)"
+                        % (int(m["launch__grid_size"][0]), os.path.basename(path), m["lts__t_sector_hit_rate.pct"][0],
+                           m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"][0]))
     except Exception:
         pass
     # executed FP64 tensor flops of one build (what the DMMA pipe issues, padding included) from the staged slice

@@ -144,3 +144,16 @@ def test_pole_sharded_schedule_covers_every_pair_once(nocc, nranks, sb):
         assert stats[r, 1] == (nranks - 1) * (hi - lo)
     if nocc >= 8 * nranks:
         assert stats[:, 0].max() <= 1.15 * stats[:, 0].min()
+
+
+def test_pole_sharded_sample_is_a_subset_of_the_schedule():
+    """shard_step_limit (the benchmark sample of a pole-sharded build): the sampled schedule forms a subset of the pairs,
+    each at most once, every rank still talks to every other rank, and limit >= the number of sub-blocks is the full one."""
+    nocc, nranks, sb = 97, 4, 5
+    full, st_full = lib.shard_cover(nocc, nranks, sb)
+    part, st_part = lib.shard_cover(nocc, nranks, sb, limit=2)
+    assert part.max() == 1 and np.all(part <= full)
+    assert 0 < part.sum() < full.sum()
+    assert np.all(st_part[:, 1] > 0) and np.all(st_part[:, 1] < st_full[:, 1])
+    same, _ = lib.shard_cover(nocc, nranks, sb, limit=100)
+    assert np.array_equal(same, full)
