@@ -29,6 +29,8 @@ RHF_CASES = [
     (5, 70, 50, 77, 5, 0, 5),         # ragged single x-block (10 row blocks) with wide column blocks
     (6, 130, 90, 172, 6, 1, 5),       # full x-block + 44-row remainder, three column blocks, slice
     (9, 64, 300, 140, 7, 0, 9),       # 12-row remainder
+    (5, 128, 90, 111, 8, 0, 5),       # ragged single x-block of 14 row blocks (quad tiles), two 64-column blocks
+    (6, 72, 60, 223, 9, 1, 6),        # full x-block + 95-row remainder (12 row blocks: quad tiles), 64 + 8 columns, slice
 ]
 # (nocc_a, nvir_a, nocc_b, nvir_b, naux, nphys, seed, istart, iend)
 UHF_CASES = [
@@ -37,6 +39,7 @@ UHF_CASES = [
     (8, 20, 7, 21, 60, 28, 2, 2, 5),
     (5, 33, 6, 17, 75, 40, 3, 0, 5),
     (5, 66, 4, 71, 60, 150, 4, 0, 5),  # nphys = 128 + 22
+    (5, 64, 4, 70, 60, 105, 5, 0, 5),  # nphys = 105: 14 row blocks (quad tiles)
 ]
 
 
