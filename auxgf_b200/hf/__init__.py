@@ -1,1 +1,1 @@
-from .model import ModelRHF, ModelUHF, Molecule  # noqa: F401
+from .model import ModelRHF, ModelUHF, ArraysRHF, ArraysUHF, Molecule, from_pyscf  # noqa: F401

@@ -187,3 +187,74 @@ class ModelUHF:
     @staticmethod
     def energy_1body(h1e, rdm1, fock):
         return 0.5 * sum(np.sum(rdm1[s] * (h1e[s] + fock[s])) for s in range(2))
+
+
+# ---- the same protocol from converged arrays (any SCF program) -----------------------------------------------
+class ArraysRHF(ModelRHF):
+    """Closed-shell ``hf`` object from a converged density-fitted SCF given as arrays: ``lpq_ao`` (naux, nao, nao) DF
+    tensor, ``h1e_ao`` core Hamiltonian, ``mo_coeff`` (C^T S C = 1; the AO basis need not be orthonormal), ``mo_energy``,
+    number of doubly occupied orbitals, nuclear repulsion and total energy."""
+
+    def __init__(self, lpq_ao, h1e_ao, mo_coeff, mo_energy, nocc, e_nuc=0.0, e_tot=None, basis="arrays"):
+        lpq_ao = np.asarray(lpq_ao, dtype=np.float64); h1e_ao = np.asarray(h1e_ao, dtype=np.float64)
+        self.nao, self.nocc_hf, self.naux = h1e_ao.shape[0], int(nocc), lpq_ao.shape[0]
+        assert lpq_ao.shape == (self.naux, self.nao, self.nao)
+        self.mol = Molecule(e_nuc=e_nuc, basis=basis)
+        self._lpq_ao, self._h1e_ao = lpq_ao, h1e_ao
+        self.c = np.asarray(mo_coeff, dtype=np.float64)
+        self.e = np.asarray(mo_energy, dtype=np.float64)
+        self.occ = np.zeros(self.e.size); self.occ[:self.nocc_hf] = 2.0
+        self.e_nuc = float(e_nuc)
+        dm = 2 * self.c[:, :self.nocc_hf] @ self.c[:, :self.nocc_hf].T
+        j, k = _jk(lpq_ao, dm)
+        self.e_elec = 0.5 * np.sum(dm * (2 * h1e_ao + j - 0.5 * k))
+        self.e_tot = float(e_tot) if e_tot is not None else self.e_elec + self.e_nuc
+        self._done = True
+
+    def run(self, *args, **kwargs):
+        return self
+
+
+class ArraysUHF(ModelUHF):
+    """Open-shell counterpart of ``ArraysRHF``: ``mo_coeff``, ``mo_energy`` are (2, ...) stacks (alpha, beta)."""
+
+    def __init__(self, lpq_ao, h1e_ao, mo_coeff, mo_energy, nalph, nbeta, e_nuc=0.0, e_tot=None, basis="arrays"):
+        lpq_ao = np.asarray(lpq_ao, dtype=np.float64); h1e_ao = np.asarray(h1e_ao, dtype=np.float64)
+        self.nao, self.nalph, self.nbeta, self.naux = h1e_ao.shape[0], int(nalph), int(nbeta), lpq_ao.shape[0]
+        self.mol = Molecule(e_nuc=e_nuc, basis=basis)
+        self._lpq_ao, self._h1e_ao = lpq_ao, h1e_ao
+        self.c = np.asarray(mo_coeff, dtype=np.float64)
+        self.e = np.asarray(mo_energy, dtype=np.float64)
+        self.occ = np.zeros((2, self.e.shape[1])); self.occ[0, :self.nalph] = 1; self.occ[1, :self.nbeta] = 1
+        self.e_nuc = float(e_nuc)
+        dm = np.stack([self.c[s][:, :n] @ self.c[s][:, :n].T for s, n in enumerate((self.nalph, self.nbeta))])
+        f = self._fock_ao(lpq_ao, h1e_ao, dm)
+        self.e_elec = 0.5 * sum(np.sum(dm[s] * (h1e_ao + f[s])) for s in range(2))
+        self.e_tot = float(e_tot) if e_tot is not None else self.e_elec + self.e_nuc
+
+    def run(self, *args, **kwargs):
+        return self
+
+
+def from_pyscf(mf):
+    """``hf`` object for the AGF2 drivers from a converged density-fitted ``pyscf.scf.RHF`` / ``UHF`` (the provider the
+    reference wraps in auxgf/hf/hf.py:99-144): core Hamiltonian, MO coefficients / energies and the Cholesky-like DF
+    tensor ``mf.with_df._cderi`` unpacked to (naux, nao, nao).  PySCF cannot be installed in the image this package is
+    developed in, so this adapter is exercised only through ``ArraysRHF`` / ``ArraysUHF`` (tests/test_drivers_cpu.py)."""
+    try:
+        from pyscf import lib as pyscf_lib
+    except ImportError as exc:         # pragma: no cover
+        raise ImportError("from_pyscf needs PySCF; use ModelRHF / ModelUHF or ArraysRHF / ArraysUHF without it") from exc
+    if getattr(mf, "with_df", None) is None:
+        mf = mf.density_fit()
+        mf.run()
+    if mf.with_df._cderi is None:
+        mf.with_df.build()
+    lpq = pyscf_lib.unpack_tril(np.asarray(mf.with_df._cderi))
+    h1e = mf.get_hcore()
+    e_nuc = mf.mol.energy_nuc()
+    mo_coeff, mo_energy = np.asarray(mf.mo_coeff), np.asarray(mf.mo_energy)
+    if mo_coeff.ndim == 2:
+        return ArraysRHF(lpq, h1e, mo_coeff, mo_energy, int(mf.mol.nelectron // 2), e_nuc, mf.e_tot, basis=mf.mol.basis)
+    nalph, nbeta = mf.mol.nelec
+    return ArraysUHF(lpq, h1e, mo_coeff, mo_energy, nalph, nbeta, e_nuc, mf.e_tot, basis=mf.mol.basis)

@@ -225,3 +225,30 @@ def test_two_rank_sharding_gloo(oracle_backend):
         p.join(timeout=60)
     for rank, e_mp2, e_tot in res:
         assert abs(e_mp2 - g.e_mp2) < 1e-10 and abs(e_tot - g.e_tot) < 1e-9
+
+
+def test_hf_from_arrays_matches_model_and_is_basis_invariant(oracle_backend):
+    """ArraysRHF / ArraysUHF (what from_pyscf builds): the same converged SCF handed over as arrays gives the same
+    protocol quantities and the same AGF2 energies -- also in a non-orthonormal AO basis (C^T S C = 1 only), which is
+    what a real SCF program provides."""
+    from auxgf_b200.agf2 import OptRAGF2, OptUAGF2
+    from auxgf_b200.hf import ArraysRHF, ArraysUHF
+    m = ModelRHF(nao=9, nocc=3, naux=20, seed=5).run()
+    rng = np.random.default_rng(0)
+    x = np.eye(9) + 0.2 * rng.standard_normal((9, 9))            # AO basis change: phi' = phi X
+    xi = np.linalg.inv(x)
+    lpq = np.einsum("Qpq,pa,qb->Qab", m._lpq_ao, x, x)
+    h1e = x.T @ m._h1e_ao @ x
+    for a in (ArraysRHF(m._lpq_ao, m._h1e_ao, m.c, m.e, 3, m.e_nuc), ArraysRHF(lpq, h1e, xi @ m.c, m.e, 3, m.e_nuc)):
+        assert abs(a.e_tot - m.e_tot) < 1e-10 and a.nelec == m.nelec and abs(a.chempot - m.chempot) < 1e-14
+        assert np.abs(a.h1e_mo - m.h1e_mo).max() < 1e-10 and np.abs(a.eri_mo - m.eri_mo).max() < 1e-10
+        assert np.abs(a.get_fock(m.rdm1_mo) - np.diag(m.e)).max() < 1e-9
+        g, r = OptRAGF2(a, verbose=False, maxiter=2), OptRAGF2(m, verbose=False, maxiter=2)
+        g.run(); r.run()
+        assert abs(g.e_mp2 - r.e_mp2) < 1e-10 and abs(g.e_tot - r.e_tot) < 1e-8
+    u = ModelUHF(nao=8, nalph=3, nbeta=2, naux=18, seed=6).run()
+    au = ArraysUHF(u._lpq_ao, u._h1e_ao, u.c, u.e, 3, 2, u.e_nuc)
+    assert abs(au.e_tot - u.e_tot) < 1e-10 and au.nelec == 5
+    assert np.abs(au.eri_mo - u.eri_mo).max() < 1e-12 and np.abs(au.get_fock(u.rdm1_mo) - u.get_fock(u.rdm1_mo)).max() < 1e-12
+    g, r = OptUAGF2(au, verbose=False, maxiter=1), OptUAGF2(u, verbose=False, maxiter=1)
+    assert abs(g.e_mp2 - r.e_mp2) < 1e-10
