@@ -260,11 +260,11 @@ extern "C" int agf2_b200_get_jk(agf2_b200_eri* h, const double* rdm1, double* j_
     for (int64_t q0 = 0; q0 < N; q0 += qblk) {
         const int64_t nq = std::min(qblk, N - q0);
         const double* Lb = h->full + q0 * PP;
-        Gemm g1;                                       // T[Q, p, s] = sum_r L[Q, p, r] D[r, s]
-        g1.a = Lb; g1.a_rows = P; g1.lda = ldp; g1.a_third = PP;
-        g1.b = Dt; g1.b_rows = P; g1.ldb = ldp; g1.b_third = 0;
-        g1.k = P; g1.nbatch = nq;
-        g1.c = T; g1.ldc = ldp; g1.c_batch = PP;
+        Gemm g1;                                       // T[(Q, p), s] = sum_r L[(Q, p), r] D[r, s]: the rows (Q, p) of the
+        g1.a = Lb; g1.a_rows = nq * P; g1.lda = ldp;   // block are equally spaced, so this is ONE tall GEMM (a batch of nq
+        g1.b = Dt; g1.b_rows = P; g1.ldb = ldp;        // small ones would pad every nphys rows to the 256-row tile)
+        g1.k = P;
+        g1.c = T; g1.ldc = ldp;
         if (int r = run_gemm(c, g1, st)) return r;
         Gemm g2;                                       // K[p, q] (+)= sum_{Q, s} T[Q, p, s] L[Q, q, s]
         g2.a = T; g2.a_rows = P; g2.lda = ldp; g2.a_third = PP;
